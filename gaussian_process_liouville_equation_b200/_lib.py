@@ -1,0 +1,157 @@
+"""ctypes binding of libgple_b200.so (the C-ABI declared in include/gple_b200.h).
+
+There is deliberately no CPU fallback: if the CUDA library cannot be loaded, or no CUDA device is
+present, every compute entry point raises.  torch is NOT required here; arguments may be numpy arrays
+(host pointers, copied in/out by the library) or anything exposing ``data_ptr()`` (torch CUDA tensors,
+passed through as device pointers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgple_b200.so")
+
+OK, ERR_ARG, ERR_NOT_SPD, ERR_CUDA, ERR_STATE = 0, 1, 2, 3, 4
+CALC_ERROR, CALC_AVERAGE, CALC_DERIVATIVE = 1, 2, 4
+SAC, DAC, ECR = 0, 1, 2
+FIELD_INVERSE, FIELD_INV_LABEL, FIELD_LABEL, FIELD_UPPER_LEFT, FIELD_LOWER_LEFT, FIELD_INV_LABEL_DERIV = 1, 2, 3, 4, 5, 8
+
+_vp, _dp, _sz = C.c_void_p, C.c_void_p, C.c_size_t  # double* passed as raw addresses (host or device)
+
+
+class RealScalars(C.Structure):
+    _fields_ = [("rescale", C.c_double), ("error", C.c_double), ("population", C.c_double), ("first_order", C.c_double * 2),
+                ("purity", C.c_double), ("magnitude", C.c_double), ("d_error", C.c_double * 4), ("d_population", C.c_double * 4),
+                ("d_purity", C.c_double * 4)]
+
+
+class ComplexScalars(C.Structure):
+    _fields_ = [("rescale", C.c_double), ("error", C.c_double), ("purity", C.c_double), ("magnitude", C.c_double),
+                ("d_error", C.c_double * 8), ("d_purity", C.c_double * 8)]
+
+
+# name -> (restype, argtypes); must list every symbol of include/gple_b200.h (tests/test_abi.py checks this)
+SIGNATURES = {
+    "gple_version": (C.c_char_p, []),
+    "gple_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "gple_ctx_destroy": (C.c_int, [_vp]),
+    "gple_ctx_set_stream": (C.c_int, [_vp, _vp]),
+    "gple_ctx_sync": (C.c_int, [_vp]),
+    "gple_last_error": (C.c_char_p, [_vp]),
+    "gple_launch_count": (C.c_ulonglong, [_vp]),
+    "gple_kernel_real": (C.c_int, [_vp, _dp, _sz, _dp, _sz, _dp, C.c_int, _dp, _dp]),
+    "gple_kernel_complex": (C.c_int, [_vp, _dp, _sz, _dp, _sz, _dp, C.c_int, _dp, _dp]),
+    "gple_train_real": (C.c_int, [_vp, _dp, _dp, _sz, _dp, C.c_uint, C.POINTER(_vp), C.POINTER(RealScalars)]),
+    "gple_train_complex": (C.c_int, [_vp, _dp, _dp, _sz, _dp, C.c_uint, C.POINTER(_vp), C.POINTER(ComplexScalars)]),
+    "gple_model_get": (C.c_int, [_vp, _vp, C.c_int, _dp]),
+    "gple_model_is_complex": (C.c_int, [_vp]),
+    "gple_model_size": (_sz, [_vp]),
+    "gple_model_destroy": (C.c_int, [_vp, _vp]),
+    "gple_predict_real": (C.c_int, [_vp, _vp, _dp, _sz, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "gple_predict_complex": (C.c_int, [_vp, _vp, _dp, _sz, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "gple_loose_function": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp, _dp, _sz, _dp, _dp, _sz, _dp]),
+    "gple_pes": (C.c_int, [_vp, C.c_int, _dp, _sz, _dp, _dp, _dp]),
+    "gple_evolve": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, _dp, _sz, _dp, _sz, C.c_double, C.c_double]),
+    "gple_new_point_predict": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),
+    "gple_observables": (C.c_int, [_vp, C.c_int, _dp, _sz, C.c_double, C.c_int, _dp]),
+    "gple_measure_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class GpleError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"gple status {status}: {message}")
+        self.status = status
+
+
+def addr(a):
+    """Raw address of a numpy array (host) or of an object with data_ptr() (device tensor); None -> NULL."""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"], "pass C-contiguous numpy arrays"
+    return a.ctypes.data
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def c128(a):
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+class Context:
+    """One CUDA device + stream (gple_ctx).  Fails loudly without a GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.gple_ctx_create(int(device), C.byref(h))
+        if rc != OK:
+            raise GpleError(rc, "gple_ctx_create failed: no usable CUDA device (this library has no CPU fallback)")
+        self.h = h
+
+    def check(self, rc, allow=()):
+        if rc != OK and rc not in allow:
+            raise GpleError(rc, self.lib.gple_last_error(self.h).decode())
+        return rc
+
+    def set_stream(self, stream_ptr):
+        self.check(self.lib.gple_ctx_set_stream(self.h, stream_ptr))
+
+    def sync(self):
+        self.check(self.lib.gple_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.gple_launch_count(self.h))
+
+    def fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self.check(self.lib.gple_measure_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gple_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default = None
+
+
+def default_context() -> Context:
+    global _default
+    if _default is None:
+        _default = Context(int(os.environ.get("LOCAL_RANK", "0")) if "GPLE_DEVICE" not in os.environ else int(os.environ["GPLE_DEVICE"]))
+    return _default

@@ -1,0 +1,624 @@
+// extern "C" boundary of libgple_b200.so (declared in include/gple_b200.h).
+#include "chol.cuh"
+#include "evolve.cuh"
+#include "gpr.cuh"
+
+#include <exception>
+
+using namespace gple;
+
+namespace
+{
+template <typename F>
+int guarded(gple_ctx* ctx, F&& f)
+{
+	if (ctx == nullptr)
+	{
+		return GPLE_ERR_ARG;
+	}
+	try
+	{
+		GPLE_CUDA(cudaSetDevice(ctx->device));
+		return f();
+	}
+	catch (const CudaError& e)
+	{
+		char buf[512];
+		std::snprintf(buf, sizeof(buf), "%s failed at %s:%d: %s", e.what, e.file, e.line, cudaGetErrorString(e.code));
+		ctx->last_error = buf;
+		cudaGetLastError();
+		return GPLE_ERR_CUDA;
+	}
+	catch (const ArgError& e)
+	{
+		ctx->last_error = e.what;
+		return GPLE_ERR_ARG;
+	}
+	catch (const std::exception& e)
+	{
+		ctx->last_error = e.what();
+		return GPLE_ERR_CUDA;
+	}
+}
+
+void require(bool ok, const char* what)
+{
+	if (!ok)
+	{
+		throw ArgError{what};
+	}
+}
+
+void sync(gple_ctx* ctx)
+{
+	GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- FP64 peak probes: register-resident dependent chains, enough independent chains to fill the pipes ----
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, const int iters)
+{
+	double acc[16][2];
+#pragma unroll
+	for (int i = 0; i < 16; i++)
+	{
+		acc[i][0] = acc[i][1] = 0.0;
+	}
+	const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+	for (int it = 0; it < iters; it++)
+	{
+#pragma unroll
+		for (int i = 0; i < 16; i++)
+		{
+			gemm::dmma884(acc[i], a, b);
+		}
+	}
+	double s = 0.0;
+#pragma unroll
+	for (int i = 0; i < 16; i++)
+	{
+		s += acc[i][0] + acc[i][1];
+	}
+	if (s == 12345.678)
+	{
+		out[0] = s;
+	}
+}
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, const int iters)
+{
+	double acc[16];
+#pragma unroll
+	for (int i = 0; i < 16; i++)
+	{
+		acc[i] = threadIdx.x * 1e-3 + i;
+	}
+	const double a = 1.0 + 1e-12, b = 1e-9;
+	for (int it = 0; it < iters; it++)
+	{
+#pragma unroll
+		for (int i = 0; i < 16; i++)
+		{
+			acc[i] = fma(acc[i], a, b);
+		}
+	}
+	double s = 0.0;
+#pragma unroll
+	for (int i = 0; i < 16; i++)
+	{
+		s += acc[i];
+	}
+	if (s == 12345.678)
+	{
+		out[0] = s;
+	}
+}
+} // namespace
+
+extern "C"
+{
+	const char* gple_version(void)
+	{
+		return "gple_b200 0.1 (sm_100a)";
+	}
+
+	int gple_ctx_create(int device, gple_ctx** out)
+	{
+		if (out == nullptr)
+		{
+			return GPLE_ERR_ARG;
+		}
+		*out = nullptr;
+		int count = 0;
+		if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+		{
+			cudaGetLastError();
+			return GPLE_ERR_CUDA; // no CUDA device: there is deliberately no CPU fallback
+		}
+		gple_ctx* ctx = new gple_ctx();
+		ctx->device = device;
+		const int rc = guarded(
+			ctx,
+			[&]() -> int
+			{
+				GPLE_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+				ctx->stream = ctx->own_stream;
+				ctx->h_pinned_count = 256;
+				GPLE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pinned), ctx->h_pinned_count * sizeof(double)));
+				cudaDeviceProp prop{};
+				GPLE_CUDA(cudaGetDeviceProperties(&prop, device));
+				ctx->num_sms = prop.multiProcessorCount;
+				gpr_setup_attributes();
+				return GPLE_OK;
+			}
+		);
+		if (rc != GPLE_OK)
+		{
+			std::fprintf(stderr, "gple_ctx_create: %s\n", ctx->last_error.c_str());
+			delete ctx;
+			return rc;
+		}
+		*out = ctx;
+		return GPLE_OK;
+	}
+
+	int gple_ctx_destroy(gple_ctx* ctx)
+	{
+		if (ctx == nullptr)
+		{
+			return GPLE_ERR_ARG;
+		}
+		cudaSetDevice(ctx->device);
+		cudaStreamSynchronize(ctx->stream);
+		ctx->ws.release();
+		if (ctx->h_pinned != nullptr)
+		{
+			cudaFreeHost(ctx->h_pinned);
+		}
+		if (ctx->own_stream != nullptr)
+		{
+			cudaStreamDestroy(ctx->own_stream);
+		}
+		delete ctx;
+		return GPLE_OK;
+	}
+
+	int gple_ctx_set_stream(gple_ctx* ctx, void* stream)
+	{
+		if (ctx == nullptr)
+		{
+			return GPLE_ERR_ARG;
+		}
+		ctx->stream = stream != nullptr ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
+		return GPLE_OK;
+	}
+
+	int gple_ctx_sync(gple_ctx* ctx)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	const char* gple_last_error(const gple_ctx* ctx)
+	{
+		return ctx != nullptr ? ctx->last_error.c_str() : "null context";
+	}
+
+	unsigned long long gple_launch_count(const gple_ctx* ctx)
+	{
+		return ctx != nullptr ? ctx->launches : 0ull;
+	}
+
+	int gple_kernel_real(gple_ctx* ctx, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[4], int same_set, double* K_out, double* dK_out)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(XL != nullptr && XR != nullptr && theta != nullptr && K_out != nullptr && nL > 0 && nR > 0, "gple_kernel_real: null argument or empty set");
+				DeviceArray<double> l(ctx, XL, 2 * nL, false), r(ctx, XR, 2 * nR, false), k(ctx, K_out, nL * nR, true), dk(ctx, dK_out, 4 * nL * nR, true);
+				kernel_real_device(ctx, l.dev, int(nL), r.dev, int(nR), theta, same_set, k.dev, dk.dev);
+				k.finish();
+				dk.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_kernel_complex(gple_ctx* ctx, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[8], int same_set, double* K_out, double* Kt_out)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(XL != nullptr && XR != nullptr && theta != nullptr && K_out != nullptr && Kt_out != nullptr && nL > 0 && nR > 0, "gple_kernel_complex: null argument or empty set");
+				DeviceArray<double> l(ctx, XL, 2 * nL, false), r(ctx, XR, 2 * nR, false), k(ctx, K_out, nL * nR, true), kt(ctx, Kt_out, 2 * nL * nR, true);
+				kernel_complex_device(ctx, l.dev, int(nL), r.dev, int(nR), theta, same_set, k.dev, kt.dev);
+				k.finish();
+				kt.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_train_real(gple_ctx* ctx, const double* X, const double* y, size_t N, const double theta[4], unsigned flags, gple_model** model, gple_real_scalars* out)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(X != nullptr && y != nullptr && theta != nullptr && model != nullptr && N > 0, "gple_train_real: null argument or empty training set");
+				*model = nullptr;
+				return train_real(ctx, X, y, N, theta, flags, model, out);
+			}
+		);
+	}
+
+	int gple_train_complex(gple_ctx* ctx, const double* X, const double* y, size_t N, const double theta[8], unsigned flags, gple_model** model, gple_complex_scalars* out)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(X != nullptr && y != nullptr && theta != nullptr && model != nullptr && N > 0, "gple_train_complex: null argument or empty training set");
+				*model = nullptr;
+				return train_complex(ctx, X, y, N, theta, flags, model, out);
+			}
+		);
+	}
+
+	int gple_model_is_complex(const gple_model* m)
+	{
+		return m != nullptr ? m->is_complex : -1;
+	}
+	size_t gple_model_size(const gple_model* m)
+	{
+		return m != nullptr ? m->N : 0;
+	}
+	int gple_model_destroy(gple_ctx* ctx, gple_model* m)
+	{
+		if (ctx != nullptr)
+		{
+			cudaSetDevice(ctx->device);
+			cudaStreamSynchronize(ctx->stream);
+		}
+		free_model(m);
+		return GPLE_OK;
+	}
+
+	int gple_model_get(gple_ctx* ctx, const gple_model* cm, int which, double* out)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(cm != nullptr && out != nullptr, "gple_model_get: null argument");
+				gple_model* m = const_cast<gple_model*>(cm);
+				const size_t N = m->N, Np = size_t(m->Np), n = size_t(m->n);
+				std::vector<double> h;
+				auto fetch = [&](const double* d, size_t count)
+				{
+					h.resize(count);
+					GPLE_CUDA(cudaMemcpyAsync(h.data(), d, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+					sync(ctx);
+				};
+				std::vector<double> res;
+				if (!m->is_complex)
+				{
+					if (which == GPLE_FIELD_INVERSE)
+					{
+						ensure_full_inverse(ctx, m);
+						fetch(m->Kinv, n * n);
+						res.resize(N * N);
+						for (size_t c = 0; c < N; c++)
+						{
+							for (size_t r = 0; r < N; r++)
+							{
+								res[c * N + r] = h[r * n + c];
+							}
+						}
+					}
+					else if (which == GPLE_FIELD_INV_LABEL || which == GPLE_FIELD_LABEL)
+					{
+						fetch(which == GPLE_FIELD_LABEL ? m->label : m->v, n);
+						res.assign(h.begin(), h.begin() + N);
+					}
+					else if (which >= GPLE_FIELD_INV_LABEL_DERIV && which < GPLE_FIELD_INV_LABEL_DERIV + 4 && m->dv != nullptr)
+					{
+						fetch(m->dv + size_t(which - GPLE_FIELD_INV_LABEL_DERIV) * n, n);
+						res.assign(h.begin(), h.begin() + N);
+					}
+					else
+					{
+						return GPLE_ERR_STATE;
+					}
+				}
+				else
+				{
+					if (which == GPLE_FIELD_INV_LABEL || which == GPLE_FIELD_LABEL)
+					{
+						// v = (wr + i wi) / 2 ; label = yr + i yi
+						fetch(which == GPLE_FIELD_LABEL ? m->label : m->v, n);
+						const double f = which == GPLE_FIELD_LABEL ? 1.0 : 0.5;
+						res.resize(2 * N);
+						for (size_t i = 0; i < N; i++)
+						{
+							res[2 * i] = f * h[i];
+							res[2 * i + 1] = f * h[Np + i];
+						}
+					}
+					else if (which == GPLE_FIELD_UPPER_LEFT || which == GPLE_FIELD_LOWER_LEFT)
+					{
+						// P = (Mrr + Mii + i (Mir - Mri)) / 4 ; Q = (Mrr - Mii - i (Mir + Mri)) / 4 with M = C^-1
+						ensure_full_inverse(ctx, m);
+						fetch(m->Kinv, n * n);
+						res.resize(2 * N * N);
+						const double sg = which == GPLE_FIELD_UPPER_LEFT ? 1.0 : -1.0;
+						for (size_t c = 0; c < N; c++)
+						{
+							for (size_t r = 0; r < N; r++)
+							{
+								const double mrr = h[r * n + c], mii = h[(Np + r) * n + Np + c], mri = h[r * n + Np + c], mir = h[(Np + r) * n + c];
+								res[2 * (c * N + r)] = 0.25 * (mrr + sg * mii);
+								res[2 * (c * N + r) + 1] = 0.25 * (sg * mir - mri);
+							}
+						}
+					}
+					else
+					{
+						return GPLE_ERR_STATE;
+					}
+				}
+				// `out` may be a device pointer as well
+				DeviceArray<double> o(ctx, out, res.size(), true);
+				if (o.owned)
+				{
+					std::memcpy(out, res.data(), res.size() * sizeof(double));
+				}
+				else
+				{
+					GPLE_CUDA(cudaMemcpyAsync(o.dev, res.data(), res.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+					sync(ctx);
+				}
+				return GPLE_OK;
+			}
+		);
+	}
+
+	static int predict_any(gple_ctx* ctx, const gple_model* m, int want_complex, const double* Xq, size_t Q, const double* yq, double* pred_out, double* var_out, double* cutoff_out, double* err_out, double* derr_out)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(m != nullptr && Xq != nullptr && Q > 0, "gple_predict: null argument or no query point");
+				require(m->is_complex == want_complex, "gple_predict: model kind does not match the entry point");
+				const size_t w = m->is_complex ? 2 : 1;
+				DeviceArray<double> xq(ctx, Xq, 2 * Q, false), y(ctx, yq, w * Q, false);
+				DeviceArray<double> pred(ctx, pred_out, w * Q, true), var(ctx, var_out, Q, true), cut(ctx, cutoff_out, w * Q, true);
+				const bool want_grad = derr_out != nullptr && yq != nullptr;
+				double* d_cut = cut.dev;
+				if (want_grad && d_cut == nullptr)
+				{
+					d_cut = ctx->ws.get<double>("pred.cut_tmp", w * Q);
+				}
+				double* d_err = (err_out != nullptr && yq != nullptr) ? ctx->ws.get<double>("pred.err", 8) : nullptr;
+				predict_device(ctx, m, xq.dev, Q, y.dev, pred.dev, var.dev, d_cut, d_err);
+				pred.finish();
+				var.finish();
+				cut.finish();
+				if (d_err != nullptr)
+				{
+					GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 128, d_err, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+				}
+				sync(ctx);
+				if (d_err != nullptr)
+				{
+					*err_out = ctx->h_pinned[128];
+				}
+				if (want_grad)
+				{
+					validation_gradient(ctx, m, xq.dev, Q, y.dev, d_cut, derr_out);
+				}
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_predict_real(gple_ctx* ctx, const gple_model* m, const double* Xq, size_t Q, const double* yq, double* pred_out, double* var_out, double* cutoff_out, double* err_out, double* derr_out)
+	{
+		return predict_any(ctx, m, 0, Xq, Q, yq, pred_out, var_out, cutoff_out, err_out, derr_out);
+	}
+	int gple_predict_complex(gple_ctx* ctx, const gple_model* m, const double* Xq, size_t Q, const double* yq, double* pred_out, double* var_out, double* cutoff_out, double* err_out, double* derr_out)
+	{
+		return predict_any(ctx, m, 1, Xq, Q, yq, pred_out, var_out, cutoff_out, err_out, derr_out);
+	}
+
+	int gple_loose_function(gple_ctx* ctx, const double* x, int nparam, double* grad, const double* X, const double* y, size_t N, const double* Xe, const double* ye, size_t M, double* value)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(x != nullptr && X != nullptr && y != nullptr && Xe != nullptr && ye != nullptr && value != nullptr && N > 0 && M > 0, "gple_loose_function: null argument");
+				require(nparam == 4 || nparam == 8, "gple_loose_function: nparam must be 4 (real) or 8 (complex)");
+				const unsigned flags = GPLE_CALC_ERROR | (grad != nullptr ? unsigned(GPLE_CALC_DERIVATIVE) : 0u);
+				gple_model* m = nullptr;
+				double trn_err = 0.0, trn_grad[8];
+				int rc;
+				if (nparam == 4)
+				{
+					gple_real_scalars s{};
+					rc = train_real(ctx, X, y, N, x, flags, &m, &s);
+					trn_err = s.error;
+					std::memcpy(trn_grad, s.d_error, 4 * sizeof(double));
+				}
+				else
+				{
+					gple_complex_scalars s{};
+					rc = train_complex(ctx, X, y, N, x, flags, &m, &s);
+					trn_err = s.error;
+					std::memcpy(trn_grad, s.d_error, 8 * sizeof(double));
+				}
+				if (rc != GPLE_OK)
+				{
+					free_model(m);
+					*value = std::nan("");
+					return rc;
+				}
+				const size_t w = nparam == 4 ? 1 : 2;
+				DeviceArray<double> xe(ctx, Xe, 2 * M, false), yc(ctx, ye, 2 * M, false);
+				// opt.cpp:451: the real kernel sees ExtraTrainingLabel.real()
+				double* yq = yc.dev;
+				if (nparam == 4)
+				{
+					yq = ctx->ws.get<double>("loose.yre", M);
+					GPLE_CUDA(cudaMemcpy2DAsync(yq, sizeof(double), yc.dev, 2 * sizeof(double), sizeof(double), M, cudaMemcpyDeviceToDevice, ctx->stream));
+				}
+				double* d_err = ctx->ws.get<double>("pred.err", 8);
+				double* d_cut = grad != nullptr ? ctx->ws.get<double>("pred.cut_tmp", w * M) : nullptr;
+				predict_device(ctx, m, xe.dev, M, yq, nullptr, nullptr, d_cut, d_err);
+				GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 128, d_err, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+				sync(ctx);
+				*value = trn_err + ctx->h_pinned[128];
+				if (grad != nullptr)
+				{
+					double vg[8];
+					validation_gradient(ctx, m, xe.dev, M, yq, d_cut, vg);
+					for (int p = 0; p < nparam; p++)
+					{
+						grad[p] = trn_grad[p] + vg[p];
+					}
+				}
+				free_model(m);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_pes(gple_ctx* ctx, int pes_model, const double* x, size_t n, double* E, double* F, double* D)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(x != nullptr && E != nullptr && F != nullptr && D != nullptr && n > 0, "gple_pes: null argument");
+				require(pes_model >= GPLE_SAC && pes_model <= GPLE_ECR, "gple_pes: unknown model");
+				DeviceArray<double> dx(ctx, x, n, false), e(ctx, E, 2 * n, true), f(ctx, F, 3 * n, true), d(ctx, D, n, true);
+				pes_device(ctx, pes_model, dx.dev, n, e.dev, f.dev, d.dev);
+				e.finish();
+				f.finish();
+				d.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_evolve(gple_ctx* ctx, int pes_model, const gple_model* m00, const gple_model* m10, const gple_model* m11, double* pts00, size_t n00, double* pts10, size_t n10, double* pts11, size_t n11, double mass, double dt)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(pes_model >= GPLE_SAC && pes_model <= GPLE_ECR, "gple_evolve: unknown model");
+				require((m00 == nullptr || !m00->is_complex) && (m11 == nullptr || !m11->is_complex) && (m10 == nullptr || m10->is_complex), "gple_evolve: diagonal elements take real models, rho10 a complex model");
+				require((n00 == 0 || pts00 != nullptr) && (n10 == 0 || pts10 != nullptr) && (n11 == 0 || pts11 != nullptr), "gple_evolve: null point set");
+				DeviceArray<double> a(ctx, pts00, 4 * n00, false), b(ctx, pts10, 4 * n10, false), c(ctx, pts11, 4 * n11, false);
+				a.write_back = b.write_back = c.write_back = true;
+				const gple_model* models[3] = {m00, m10, m11};
+				double* d_pts[3] = {a.dev, b.dev, c.dev};
+				const size_t counts[3] = {n00, n10, n11};
+				evolve_device(ctx, pes_model, models, d_pts, counts, mass, dt);
+				a.finish();
+				b.finish();
+				c.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_new_point_predict(gple_ctx* ctx, int pes_model, const gple_model* m00, const gple_model* m10, const gple_model* m11, const double* r, size_t n, int row, int col, double mass, double dt, double* out)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(r != nullptr && out != nullptr && n > 0, "gple_new_point_predict: null argument");
+				require(row >= 0 && row < 2 && col >= 0 && col <= row, "gple_new_point_predict: (row, col) must be a lower-triangular index");
+				DeviceArray<double> dr(ctx, r, 2 * n, false), o(ctx, out, 2 * n, true);
+				const gple_model* models[3] = {m00, m10, m11};
+				new_point_predict_device(ctx, pes_model, models, dr.dev, n, row, col, mass, dt, o.dev);
+				o.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_observables(gple_ctx* ctx, int pes_model, const double* pts, size_t n, double mass, int pes_index, double out[9])
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(pts != nullptr && out != nullptr && n > 0, "gple_observables: null argument");
+				DeviceArray<double> p(ctx, pts, 4 * n, false), o(ctx, out, 9, true);
+				observables_device(ctx, pes_model, p.dev, n, mass, pes_index, o.dev);
+				o.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_measure_fp64_peak(gple_ctx* ctx, double* dmma_tflops, double* dfma_tflops)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				double* d = ctx->ws.get<double>("peak.out", 8);
+				const int iters = 4096, blocks = ctx->num_sms * 4;
+				cudaEvent_t e0, e1;
+				GPLE_CUDA(cudaEventCreate(&e0));
+				GPLE_CUDA(cudaEventCreate(&e1));
+				float ms = 0.f;
+				double best_mma = 0.0, best_fma = 0.0;
+				for (int rep = 0; rep < 4; rep++)
+				{
+					GPLE_CUDA(cudaEventRecord(e0, ctx->stream));
+					GPLE_LAUNCH(ctx, dmma_peak_kernel, blocks, 256, 0, d, iters);
+					GPLE_CUDA(cudaEventRecord(e1, ctx->stream));
+					GPLE_CUDA(cudaEventSynchronize(e1));
+					GPLE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+					best_mma = std::max(best_mma, double(blocks) * 8 * 16 * iters * 512.0 / (ms * 1e-3) / 1e12);
+					GPLE_CUDA(cudaEventRecord(e0, ctx->stream));
+					GPLE_LAUNCH(ctx, dfma_peak_kernel, blocks, 256, 0, d, iters * 4);
+					GPLE_CUDA(cudaEventRecord(e1, ctx->stream));
+					GPLE_CUDA(cudaEventSynchronize(e1));
+					GPLE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+					best_fma = std::max(best_fma, double(blocks) * 256 * 16 * (iters * 4.0) * 2.0 / (ms * 1e-3) / 1e12);
+				}
+				cudaEventDestroy(e0);
+				cudaEventDestroy(e1);
+				if (dmma_tflops != nullptr)
+				{
+					*dmma_tflops = best_mma;
+				}
+				if (dfma_tflops != nullptr)
+				{
+					*dfma_tflops = best_fma;
+				}
+				return GPLE_OK;
+			}
+		);
+	}
+}

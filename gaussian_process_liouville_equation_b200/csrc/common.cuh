@@ -1,0 +1,181 @@
+// Shared declarations of the B200 (sm_100a) GPR-MQCLE library: context, device buffers, status plumbing.
+#pragma once
+#include "../../include/gple_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace gple
+{
+constexpr int TILE = 128; // all device matrices are padded to a multiple of this
+
+inline size_t round_up(size_t n, size_t m)
+{
+	return (n + m - 1) / m * m;
+}
+
+struct CudaError
+{
+	cudaError_t code;
+	const char* what;
+	const char* file;
+	int line;
+};
+
+#define GPLE_CUDA(expr)                                                         \
+	do                                                                          \
+	{                                                                           \
+		const cudaError_t e__ = (expr);                                         \
+		if (e__ != cudaSuccess)                                                 \
+		{                                                                       \
+			throw ::gple::CudaError{e__, #expr, __FILE__, __LINE__};            \
+		}                                                                       \
+	} while (0)
+
+struct ArgError
+{
+	const char* what;
+};
+
+/// Grow-only named scratch buffers: no cudaMalloc on the steady-state path.
+struct Workspace
+{
+	std::map<std::string, std::pair<void*, size_t>> bufs;
+	void* get(const std::string& name, size_t bytes)
+	{
+		auto& e = bufs[name];
+		if (e.second < bytes)
+		{
+			if (e.first != nullptr)
+			{
+				GPLE_CUDA(cudaFree(e.first));
+				e.first = nullptr;
+				e.second = 0;
+			}
+			GPLE_CUDA(cudaMalloc(&e.first, bytes));
+			e.second = bytes;
+		}
+		return e.first;
+	}
+	template <typename T>
+	T* get(const std::string& name, size_t count)
+	{
+		return static_cast<T*>(get(name, count * sizeof(T)));
+	}
+	void release()
+	{
+		for (auto& kv : bufs)
+		{
+			if (kv.second.first != nullptr)
+			{
+				cudaFree(kv.second.first);
+			}
+		}
+		bufs.clear();
+	}
+};
+} // namespace gple
+
+struct gple_ctx
+{
+	int device = 0;
+	cudaStream_t own_stream = nullptr;
+	cudaStream_t stream = nullptr;
+	unsigned long long launches = 0;
+	std::string last_error;
+	gple::Workspace ws;
+	double* h_pinned = nullptr; // small pinned staging area for scalar read-backs
+	size_t h_pinned_count = 0;
+	int num_sms = 148;
+};
+
+namespace gple
+{
+/// RAII view of a caller array on the device: copies a host array in (and optionally back out).
+template <typename T>
+struct DeviceArray
+{
+	gple_ctx* ctx;
+	T* dev = nullptr;
+	T* host = nullptr; // non-null when the caller passed a host pointer
+	size_t count = 0;
+	bool owned = false;
+	bool write_back = false;
+
+	DeviceArray(gple_ctx* c, const T* ptr, size_t n, bool is_output): ctx(c), count(n), write_back(is_output)
+	{
+		if (ptr == nullptr || n == 0)
+		{
+			return;
+		}
+		cudaPointerAttributes at{};
+		const cudaError_t e = cudaPointerGetAttributes(&at, ptr);
+		if (e != cudaSuccess)
+		{
+			cudaGetLastError();
+		}
+		if (e == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged))
+		{
+			dev = const_cast<T*>(ptr);
+			return;
+		}
+		host = const_cast<T*>(ptr);
+		GPLE_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dev), n * sizeof(T), ctx->stream));
+		owned = true;
+		if (!is_output)
+		{
+			GPLE_CUDA(cudaMemcpyAsync(dev, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+		}
+	}
+	/// copy results back to a host caller (stream-ordered; caller syncs)
+	void finish()
+	{
+		if (owned && write_back && host != nullptr)
+		{
+			GPLE_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+		}
+	}
+	~DeviceArray()
+	{
+		if (owned && dev != nullptr)
+		{
+			cudaFreeAsync(dev, ctx->stream);
+		}
+	}
+	DeviceArray(const DeviceArray&) = delete;
+	DeviceArray& operator=(const DeviceArray&) = delete;
+	explicit operator bool() const { return dev != nullptr; }
+};
+
+#define GPLE_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+	do                                                                          \
+	{                                                                           \
+		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);        \
+		(ctx)->launches++;                                                      \
+		GPLE_CUDA(cudaGetLastError());                                          \
+	} while (0)
+
+// ---- parameter blocks passed by value to kernels -------------------------------------------------
+
+/// Gaussian ARD kernel sigma_f^2 * (exp(-1/2 sum ((dx)/l)^2) + sigma_n^2 delta): gple/kernel.h:25-28
+struct GaussParam
+{
+	double mag2;   // sigma_f^2
+	double inv_lx; // 1 / l_x
+	double inv_lp; // 1 / l_p
+	double noise2; // sigma_n^2
+};
+
+inline GaussParam make_gauss(double mag, double lx, double lp, double noise)
+{
+	return GaussParam{mag * mag, 1.0 / lx, 1.0 / lp, noise * noise};
+}
+
+} // namespace gple

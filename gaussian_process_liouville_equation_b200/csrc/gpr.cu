@@ -1,0 +1,997 @@
+// Training and batched prediction of one density-matrix element on B200 (sm_100a).
+//
+// Reference path replaced (gple/ = gaussian_process_liouville_equation/ of the reference):
+//   TrainingKernel          gple/kernel.cpp:244-479        PredictiveKernel         gple/kernel.cpp:481-544
+//   TrainingComplexKernel   gple/complex_kernel.cpp:221-592 PredictiveComplexKernel gple/complex_kernel.cpp:594-670
+//
+// Design (not a port):
+//  * K = L L^T by blocked DMMA Cholesky, W = L^-1 by blocked DMMA triangular inverse (chol.cu); K^-1 = W^T W
+//    is never formed on the prediction path.  diag(K^-1) (needed by the LOOCV error, kernel.cpp:285) is the
+//    column sum of squares of W; v = K^-1 y' = W^T (W y').
+//  * The per-query variance k** - k K^-1 k^T (kernel.cpp:496-518: one GEMV over the N x N inverse PER
+//    QUERY in the reference) becomes  k** - || W k^T ||^2 : one triangular DMMA GEMM  Z = K* W^T  over a
+//    chunk of queries with the row sum of squares fused into the epilogue -- half the flops of K* K^-1 and
+//    no cancellation inside the quadratic form.
+//  * The widely-linear complex GPR (K, K-tilde, augmented inverse blocks P, Q) is evaluated as the equivalent
+//    real process over [Re f; Im f] of order 2N, so it reuses the same Cholesky / inverse / variance kernels;
+//    P_ii, Q_ii and v of complex_kernel.cpp:264-286 are recovered from W by O(N^2) column passes.
+#include "chol.cuh"
+#include "gpr.cuh"
+#include "gpr_kernels.cuh"
+
+namespace gple
+{
+namespace
+{
+// ---------------------------------------------------------------------------------------------------
+// covariance construction
+// ---------------------------------------------------------------------------------------------------
+
+/// Lower 128-tiles of the (composite) training covariance, row-major n x n with n = nb * Np.
+/// Padding rows/columns (point index >= N) carry the identity so the factorisation stays decoupled.
+__global__ void __launch_bounds__(256) build_cov_lower_kernel(const BlockSpec spec, const double2* __restrict__ X, const int N, const int Np, const int n, double* __restrict__ K)
+{
+	const int bj = blockIdx.x, bi = blockIdx.y;
+	if (bj > bi)
+	{
+		return;
+	}
+	__shared__ double2 xr[128], xc[128];
+	const int I0 = bi * 128, J0 = bj * 128;
+	const int rb = I0 / Np, cb = J0 / Np; // a 128-tile never straddles blocks (Np is a multiple of 128)
+	const int i0 = I0 - rb * Np, j0 = J0 - cb * Np;
+	if (threadIdx.x < 128)
+	{
+		xr[threadIdx.x] = X[i0 + threadIdx.x];
+	}
+	else
+	{
+		xc[threadIdx.x - 128] = X[j0 + threadIdx.x - 128];
+	}
+	__syncthreads();
+	const GaussBlock g = spec.b[rb][cb];
+	const int c2 = (threadIdx.x & 63) * 2;
+	for (int r = threadIdx.x >> 6; r < 128; r += 4)
+	{
+		const int i = i0 + r;
+		double2 out;
+		double* o = &out.x;
+#pragma unroll
+		for (int u = 0; u < 2; u++)
+		{
+			const int j = j0 + c2 + u;
+			double val;
+			if (i < N && j < N)
+			{
+				val = gauss_value(g, xr[r], xc[c2 + u]) + (i == j ? g.diag_add : 0.0);
+			}
+			else
+			{
+				val = (I0 + r == J0 + c2 + u) ? 1.0 : 0.0;
+			}
+			o[u] = val;
+		}
+		*reinterpret_cast<double2*>(K + size_t(I0 + r) * n + J0 + c2) = out;
+	}
+}
+
+/// Rows of the test-vs-training covariance for a chunk of `rows` composite rows starting at row0, written
+/// K-contiguous (row-major rows x n) as the A operand of the variance GEMM, fused with the mean K* v
+/// (kernel.cpp:495 / complex_kernel.cpp:608).  One warp per row; lanes stream 16-byte stores.
+__global__ void __launch_bounds__(256) kstar_kernel(
+	const BlockSpec spec,
+	const double2* __restrict__ Xq,
+	const long long Q,
+	const long long row0,
+	const int rows,
+	const double2* __restrict__ Xt,
+	const int N,
+	const int Np,
+	const int n,
+	const double* __restrict__ w,
+	double* __restrict__ A,
+	double* __restrict__ pred
+)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int r = blockIdx.x * 8 + warp;
+	if (r >= rows)
+	{
+		return;
+	}
+	const long long R = row0 + r;
+	const long long m = R / spec.nb;
+	const int rb = int(R - m * spec.nb);
+	double* __restrict__ out = A + size_t(r) * n;
+	if (m >= Q)
+	{
+		for (int J = lane * 2; J < n; J += 64)
+		{
+			*reinterpret_cast<double2*>(out + J) = make_double2(0.0, 0.0);
+		}
+		return;
+	}
+	const double2 xq = Xq[m];
+	double acc = 0.0;
+	for (int cb = 0; cb < spec.nb; cb++)
+	{
+		const GaussBlock g = spec.b[rb][cb];
+		const double* __restrict__ wb = w + cb * Np;
+		double* __restrict__ ob = out + cb * Np;
+		for (int j = lane * 2; j < Np; j += 64)
+		{
+			double2 val = make_double2(0.0, 0.0);
+			if (j < N)
+			{
+				const double2 xa = Xt[j];
+				val.x = gauss_value(g, xq, xa) + ((xq.x == xa.x && xq.y == xa.y) ? g.diag_add : 0.0);
+				acc += val.x * wb[j];
+			}
+			if (j + 1 < N)
+			{
+				const double2 xb = Xt[j + 1];
+				val.y = gauss_value(g, xq, xb) + ((xq.x == xb.x && xq.y == xb.y) ? g.diag_add : 0.0);
+				acc += val.y * wb[j + 1];
+			}
+			*reinterpret_cast<double2*>(ob + j) = val;
+		}
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	}
+	if (lane == 0)
+	{
+		pred[r] = acc;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// variance GEMM:  q[r] = sum_n ( sum_{k <= n} A[r][k] W[n][k] )^2      (Z = A W^T, W lower triangular)
+// ---------------------------------------------------------------------------------------------------
+
+/// One CTA owns 128 query rows and walks all n-tiles; the cp.async pipeline runs across n-tile boundaries
+/// (flattened (n-tile, k-step) sequence) so the tensor pipe never drains.  The squared accumulators are
+/// folded into 8 per-thread row sums; no Z is ever written.
+__global__ void __launch_bounds__(gemm::THREADS, 1) var_gemm_kernel(const double* __restrict__ A, const double* __restrict__ W, const int n, double* __restrict__ q)
+{
+	using namespace gemm;
+	extern __shared__ __align__(16) double smem[];
+	double* As = smem;
+	double* Bs = smem + STAGES * A_STAGE;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
+	const int m0 = blockIdx.x * BM;
+	const int T = n / BN;
+	const double* Ag = A + size_t(m0) * n;
+
+	int l_nt = 0, l_kt = 0, l_slot = 0;
+	auto issue = [&]()
+	{
+		if (l_nt < T)
+		{
+			load_tile_kmajor(As + l_slot * A_STAGE, Ag + size_t(l_kt) * BK, size_t(n), tid);
+			load_tile_kmajor(Bs + l_slot * B_STAGE, W + size_t(l_nt) * BN * n + size_t(l_kt) * BK, size_t(n), tid);
+			l_slot = (l_slot + 1 == STAGES) ? 0 : l_slot + 1;
+			if (++l_kt == (l_nt + 1) * (BN / BK))
+			{
+				l_kt = 0;
+				l_nt++;
+			}
+		}
+		cp_async_commit();
+	};
+#pragma unroll
+	for (int s = 0; s < STAGES - 1; s++)
+	{
+		issue();
+	}
+	double rowsum[8];
+#pragma unroll
+	for (int i = 0; i < 8; i++)
+	{
+		rowsum[i] = 0.0;
+	}
+	double acc[8][4][2];
+	int c_slot = 0;
+	for (int nt = 0; nt < T; nt++)
+	{
+		zero_acc(acc);
+		const int steps = (nt + 1) * (BN / BK);
+		for (int kt = 0; kt < steps; kt++)
+		{
+			cp_async_wait<STAGES - 2>();
+			__syncthreads();
+			issue();
+			compute_stage<false>(acc, As + c_slot * A_STAGE, Bs + c_slot * B_STAGE, wm, wn, g, t);
+			c_slot = (c_slot + 1 == STAGES) ? 0 : c_slot + 1;
+		}
+#pragma unroll
+		for (int i = 0; i < 8; i++)
+		{
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+			{
+				rowsum[i] = fma(acc[i][j][0], acc[i][j][0], rowsum[i]);
+				rowsum[i] = fma(acc[i][j][1], acc[i][j][1], rowsum[i]);
+			}
+		}
+	}
+	cp_async_wait<0>();
+	__syncthreads();
+	// reduce over the 4 lanes of a quad (columns) and over the 4 column-warps
+	double* red = smem; // [4][128]
+#pragma unroll
+	for (int i = 0; i < 8; i++)
+	{
+		double s = rowsum[i];
+		s += __shfl_xor_sync(0xffffffffu, s, 1);
+		s += __shfl_xor_sync(0xffffffffu, s, 2);
+		if (t == 0)
+		{
+			red[wn * BM + wm * 64 + i * 8 + g] = s;
+		}
+	}
+	__syncthreads();
+	if (tid < BM)
+	{
+		q[m0 + tid] = (red[tid] + red[BM + tid]) + (red[2 * BM + tid] + red[3 * BM + tid]);
+	}
+}
+
+/// kernel.cpp:496-519 + kernel.h:301-332: variance, cubic gate, cutoff prediction (real element)
+__device__ __forceinline__ double gate_factor(const double pred_sq, const double abs_pred, const double var)
+{
+	if (pred_sq >= 4.0 * var) // ConnectingPoint^2 (also taken for var < 0: quirk q5)
+	{
+		return 1.0;
+	}
+	if (pred_sq <= var)
+	{
+		return 0.0;
+	}
+	const double a = abs_pred / sqrt(var);
+	return (5.0 - 2.0 * a) * (a - 1.0) * (a - 1.0);
+}
+
+__global__ void finalize_real_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double* __restrict__ pred_out, double* __restrict__ var_out, double* __restrict__ cut_out)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= rows || row0 + r >= Q)
+	{
+		return;
+	}
+	const double f = pred[r], var = prior - q[r];
+	const double gate = gate_factor(f * f, fabs(f), var);
+	if (pred_out != nullptr)
+	{
+		pred_out[row0 + r] = f;
+	}
+	if (var_out != nullptr)
+	{
+		var_out[row0 + r] = var;
+	}
+	if (cut_out != nullptr)
+	{
+		cut_out[row0 + r] = f * gate / rescale;
+	}
+}
+
+/// complex_kernel.cpp:608-643 in composite form: rows (2m, 2m+1) = (Re, Im) parts of query m
+__global__ void finalize_complex_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double2* __restrict__ pred_out, double* __restrict__ var_out, double2* __restrict__ cut_out)
+{
+	const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+	const long long m = row0 / 2 + pidx;
+	if (2 * pidx + 1 >= rows || m >= Q)
+	{
+		return;
+	}
+	const double fr = pred[2 * pidx], fi = pred[2 * pidx + 1];
+	const double var = prior - q[2 * pidx] - q[2 * pidx + 1];
+	const double ps = fr * fr + fi * fi;
+	const double gate = gate_factor(ps, hypot(fr, fi), var);
+	if (pred_out != nullptr)
+	{
+		pred_out[m] = make_double2(fr, fi);
+	}
+	if (var_out != nullptr)
+	{
+		var_out[m] = var;
+	}
+	if (cut_out != nullptr)
+	{
+		cut_out[m] = make_double2(fr * gate / rescale, fi * gate / rescale);
+	}
+}
+
+/// partial sums of (pred - rescale * y)^2 over a chunk, accumulated into acc[0] by a single block
+/// (deterministic order: chunks are processed sequentially on the stream).
+__global__ void __launch_bounds__(1024) sqerr_kernel(const double* __restrict__ pred, const int rows, const long long row0, const long long total_rows, const double* __restrict__ yq, const int y_stride, const int nb, const double rescale, double* __restrict__ acc)
+{
+	__shared__ double scratch[32];
+	double s[1] = {0.0};
+	for (int r = threadIdx.x; r < rows && row0 + r < total_rows; r += 1024)
+	{
+		const long long R = row0 + r;
+		const long long m = R / nb;
+		const int part = int(R - m * nb);
+		const double d = pred[r] - rescale * yq[m * y_stride + part];
+		s[0] = fma(d, d, s[0]);
+	}
+	block_reduce<1, 1024>(s, scratch);
+	if (threadIdx.x == 0)
+	{
+		acc[0] += s[0];
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// training: labels, v = W^T W y', diag(K^-1), scalar reductions
+// ---------------------------------------------------------------------------------------------------
+
+/// kernel.cpp:279-280 / complex_kernel.cpp:262-263.  out[0] = rescale.  label = [s Re y ; s Im y (complex only)].
+__global__ void __launch_bounds__(1024) label_kernel(const double2* __restrict__ y, const int N, const int Np, const int is_complex, double* __restrict__ label, double* __restrict__ scal)
+{
+	__shared__ double red[32];
+	__shared__ double s_rescale;
+	double mx = 0.0;
+	for (int i = threadIdx.x; i < N; i += 1024)
+	{
+		const double2 v = y[i];
+		mx = fmax(mx, is_complex ? hypot(v.x, v.y) : fabs(v.x));
+	}
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	}
+	if ((threadIdx.x & 31) == 0)
+	{
+		red[threadIdx.x >> 5] = mx;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		double m = 0.0;
+		for (int w = 0; w < 32; w++)
+		{
+			m = fmax(m, red[w]);
+		}
+		s_rescale = 10.0 / m; // RescaleMaximum, kernel.h:37
+		scal[0] = s_rescale;
+	}
+	__syncthreads();
+	const double s = s_rescale;
+	for (int i = threadIdx.x; i < Np; i += 1024)
+	{
+		const double2 v = i < N ? y[i] : make_double2(0.0, 0.0);
+		label[i] = v.x * s;
+		if (is_complex)
+		{
+			label[Np + i] = v.y * s;
+		}
+	}
+}
+
+/// z = W y (W lower triangular, row-major): one warp per row.
+__global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restrict__ W, const int n, const double* __restrict__ y, double* __restrict__ z)
+{
+	const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+	if (row >= n)
+	{
+		return;
+	}
+	const double* __restrict__ wr = W + size_t(row) * n;
+	double s = 0.0;
+	for (int k = lane * 2; k <= row; k += 64)
+	{
+		const double2 a = *reinterpret_cast<const double2*>(wr + k), b = *reinterpret_cast<const double2*>(y + k);
+		s = fma(a.x, b.x, s);
+		s = fma(a.y, b.y, s); // W[row][row + 1] == 0
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		s += __shfl_xor_sync(0xffffffffu, s, o);
+	}
+	if (lane == 0)
+	{
+		z[row] = s;
+	}
+}
+
+/// Column pass over W: v_k = sum_i W[i][k] z_i, ss_k = sum_i W[i][k]^2 (= [K^-1]_kk), and for the composite
+/// model cross_k = sum_i W[i][k] W[i][Np + k], k < Np (= [M_ri]_kk).  Rows are split over blockIdx.y and
+/// the per-slab partials are reduced by `col_reduce_kernel` (deterministic, no atomics).
+__global__ void __launch_bounds__(128) col_pass_kernel(const double* __restrict__ W, const int n, const int Np, const int want_cross, const double* __restrict__ z, const int slab, double* __restrict__ part /* [gridDim.y][3][n] */)
+{
+	const int k = blockIdx.x * 128 + threadIdx.x;
+	const int i_begin = max(blockIdx.y * slab, (k / 128) * 128), i_end = min(n, (blockIdx.y + 1) * slab);
+	double sv = 0.0, ss = 0.0, sc = 0.0;
+	const bool cross = want_cross && k < Np;
+#pragma unroll 4
+	for (int i = i_begin; i < i_end; i++)
+	{
+		const double a = W[size_t(i) * n + k];
+		sv = fma(a, z[i], sv);
+		ss = fma(a, a, ss);
+		if (cross)
+		{
+			sc = fma(a, W[size_t(i) * n + Np + k], sc);
+		}
+	}
+	double* p = part + size_t(blockIdx.y) * 3 * n;
+	p[k] = sv;
+	p[n + k] = ss;
+	p[2 * n + k] = sc;
+}
+__global__ void col_reduce_kernel(const double* __restrict__ part, const int n, const int slabs, double* __restrict__ v, double* __restrict__ ss, double* __restrict__ cross)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n)
+	{
+		return;
+	}
+	double a = 0.0, b = 0.0, c = 0.0;
+	for (int s = 0; s < slabs; s++)
+	{
+		const double* p = part + size_t(s) * 3 * n;
+		a += p[k];
+		b += p[n + k];
+		c += p[2 * n + k];
+	}
+	v[k] = a;
+	ss[k] = b;
+	if (cross != nullptr)
+	{
+		cross[k] = c;
+	}
+}
+
+/// Real element reductions.  scal[1..6] = LOOCV error, sum v, sum x v, sum p v, y'^T v, unused
+__global__ void __launch_bounds__(1024) real_scalars_kernel(const double2* __restrict__ X, const double* __restrict__ label, const double* __restrict__ v, const double* __restrict__ dinv, const int N, double* __restrict__ scal)
+{
+	__shared__ double scratch[5 * 32];
+	double s[5] = {0, 0, 0, 0, 0};
+	for (int i = threadIdx.x; i < N; i += 1024)
+	{
+		const double vi = v[i], r = vi / dinv[i];
+		const double2 x = X[i];
+		s[0] = fma(r, r, s[0]);
+		s[1] += vi;
+		s[2] = fma(x.x, vi, s[2]);
+		s[3] = fma(x.y, vi, s[3]);
+		s[4] = fma(label[i], vi, s[4]);
+	}
+	block_reduce<5, 1024>(s, scratch);
+	if (threadIdx.x == 0)
+	{
+		for (int i = 0; i < 5; i++)
+		{
+			scal[1 + i] = s[i];
+		}
+	}
+}
+
+/// Complex element reductions from the composite solution (complex_kernel.cpp:270-286, complex_kernel.h:192-204):
+/// P_ii = (Mrr + Mii) / 4, Q_ii = (Mrr - Mii) / 4 - i Mri / 2, v_i = (wr + i wi) / 2.
+/// scal[1] = LOOCV error, scal[2] = Re(y'^H v)
+__global__ void __launch_bounds__(1024) complex_scalars_kernel(const double* __restrict__ label, const double* __restrict__ w, const double* __restrict__ ss, const double* __restrict__ cross, const int N, const int Np, double* __restrict__ scal)
+{
+	__shared__ double scratch[2 * 32];
+	double s[2] = {0, 0};
+	for (int i = threadIdx.x; i < N; i += 1024)
+	{
+		const double mrr = ss[i], mii = ss[Np + i], mri = cross[i];
+		const double p = 0.25 * (mrr + mii);
+		const double qr = 0.25 * (mrr - mii), qi = -0.5 * mri;
+		const double vr = 0.5 * w[i], vi = 0.5 * w[Np + i];
+		// numerator P v - conj(Q v)
+		const double qvr = qr * vr - qi * vi, qvi = qr * vi + qi * vr;
+		const double nr = p * vr - qvr, ni = p * vi + qvi;
+		const double den = p * p - (qr * qr + qi * qi);
+		const double dr = nr / den, di = ni / den;
+		s[0] += dr * dr + di * di;
+		s[1] += label[i] * vr + label[Np + i] * vi;
+	}
+	block_reduce<2, 1024>(s, scratch);
+	if (threadIdx.x == 0)
+	{
+		scal[1] = s[0];
+		scal[2] = s[1];
+	}
+}
+
+/// Quadratic form  sum_{I,J} w_I Kaux(I,J) w_J  with Kaux generated on the fly (never stored): the purity
+/// integrals of kernel.cpp:313-335 and complex_kernel.cpp:357-377.  Each block of the covariance may be the
+/// sum of two Gaussians.  One CTA per 128 x 128 tile; per-tile partials are summed by quad_reduce_kernel.
+struct QuadSpec
+{
+	int nb;
+	GaussBlock g[2][2][2];
+};
+__global__ void __launch_bounds__(256) quadform_kernel(const QuadSpec spec, const double2* __restrict__ X, const int N, const int Np, const double* __restrict__ w, double* __restrict__ part)
+{
+	__shared__ double2 xr[128], xc[128];
+	__shared__ double wr[128], wc[128];
+	__shared__ double scratch[8];
+	const int tiles = Np / 128;
+	const int bi = blockIdx.y, bj = blockIdx.x;
+	const int rb = bi / tiles, cb = bj / tiles;
+	const int i0 = (bi - rb * tiles) * 128, j0 = (bj - cb * tiles) * 128;
+	if (threadIdx.x < 128)
+	{
+		xr[threadIdx.x] = X[i0 + threadIdx.x];
+		wr[threadIdx.x] = (i0 + threadIdx.x < N) ? w[rb * Np + i0 + threadIdx.x] : 0.0;
+	}
+	else
+	{
+		const int c = threadIdx.x - 128;
+		xc[c] = X[j0 + c];
+		wc[c] = (j0 + c < N) ? w[cb * Np + j0 + c] : 0.0;
+	}
+	__syncthreads();
+	const GaussBlock ga = spec.g[rb][cb][0], gb = spec.g[rb][cb][1];
+	double s[1] = {0.0};
+	const int c = threadIdx.x & 127;
+	for (int r = threadIdx.x >> 7; r < 128; r += 2)
+	{
+		double k = gauss_value(ga, xr[r], xc[c]);
+		if (gb.mag2 != 0.0)
+		{
+			k += gauss_value(gb, xr[r], xc[c]);
+		}
+		s[0] = fma(wr[r] * k, wc[c], s[0]);
+	}
+	block_reduce<1, 256>(s, scratch);
+	if (threadIdx.x == 0)
+	{
+		part[blockIdx.y * gridDim.x + blockIdx.x] = s[0];
+	}
+}
+__global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ part, const int count, double* __restrict__ out)
+{
+	__shared__ double scratch[32];
+	double s[1] = {0.0};
+	for (int i = threadIdx.x; i < count; i += 1024)
+	{
+		s[0] += part[i];
+	}
+	block_reduce<1, 1024>(s, scratch);
+	if (threadIdx.x == 0)
+	{
+		out[0] = s[0];
+	}
+}
+
+/// out (n x n, row-major) = transpose of in
+__global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, const int n)
+{
+	__shared__ double tile[32][33];
+	const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+	for (int r = threadIdx.y; r < 32; r += 8)
+	{
+		tile[r][threadIdx.x] = in[size_t(by + r) * n + bx + threadIdx.x];
+	}
+	__syncthreads();
+	for (int r = threadIdx.y; r < 32; r += 8)
+	{
+		out[size_t(bx + r) * n + by + threadIdx.x] = tile[threadIdx.x][r];
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// general kernel-matrix builder for the C-ABI (column-major output like Eigen)
+// ---------------------------------------------------------------------------------------------------
+
+/// KernelBase (kernel.cpp:217-242) incl. delta_kernel (kernel.cpp:8-31) and calculate_derivative
+/// (kernel.cpp:168-215): K and the four dK/dtheta, column-major nL x nR.
+__global__ void __launch_bounds__(256) kernel_real_kernel(const double2* __restrict__ XL, const int nL, const double2* __restrict__ XR, const int nR, const double mag, const double lx, const double lp, const double noise, const int same, double* __restrict__ K, double* __restrict__ dK)
+{
+	const int r = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+	if (r >= nL)
+	{
+		return;
+	}
+	const double2 a = XL[r], b = XR[c];
+	const double dx = (a.x - b.x) / lx, dp = (a.y - b.y) / lp;
+	const double gsn = exp(-(dx * dx + dp * dp) / 2.0);
+	const double delta = same ? (r == c ? 1.0 : 0.0) : ((a.x == b.x && a.y == b.y) ? 1.0 : 0.0);
+	const double k = mag * mag * (gsn + noise * noise * delta);
+	const size_t o = size_t(c) * nL + r, sz = size_t(nL) * nR;
+	K[o] = k;
+	if (dK != nullptr)
+	{
+		dK[o] = k * (2.0 / mag);
+		const bool diag = same && r == c;
+		const double gp = same ? k - (diag ? (mag * noise) * (mag * noise) : 0.0) : k;
+		dK[sz + o] = diag ? 0.0 : gp * (dx * dx / lx);
+		dK[2 * sz + o] = diag ? 0.0 : gp * (dp * dp / lp);
+		dK[3 * sz + o] = diag ? 2.0 * mag * mag * noise : 0.0;
+	}
+}
+
+/// ComplexKernelBase (complex_kernel.cpp:134-200): K (real) and the pseudo-covariance Kt (complex), column-major.
+__global__ void __launch_bounds__(256) kernel_complex_kernel(const double2* __restrict__ XL, const int nL, const double2* __restrict__ XR, const int nR, const GaussBlock gr, const GaussBlock gi, const GaussBlock gc, const double mag2, const double noise2, const int same, double* __restrict__ K, double2* __restrict__ Kt)
+{
+	const int r = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+	if (r >= nL)
+	{
+		return;
+	}
+	const double2 a = XL[r], b = XR[c];
+	const double kr = gauss_value(gr, a, b), ki = gauss_value(gi, a, b), kc = gauss_value(gc, a, b);
+	const double delta = same ? (r == c ? 1.0 : 0.0) : ((a.x == b.x && a.y == b.y) ? 1.0 : 0.0);
+	const size_t o = size_t(c) * nL + r;
+	K[o] = mag2 * (kr + ki + noise2 * delta);
+	Kt[o] = make_double2(mag2 * (kr - ki), mag2 * (2.0 * kc));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side orchestration
+// ---------------------------------------------------------------------------------------------------
+
+BlockSpec real_spec(const double* th)
+{
+	BlockSpec s{};
+	s.nb = 1;
+	s.b[0][0] = GaussBlock{th[0] * th[0], 1.0 / th[1], 1.0 / th[2], th[0] * th[0] * th[3] * th[3]};
+	return s;
+}
+
+struct ComplexSub
+{
+	double sr, si, sc;
+	double lr[2], li[2], lc[2];
+};
+/// complex_kernel.cpp:142-157
+ComplexSub complex_sub(const double* th)
+{
+	ComplexSub c{};
+	c.sr = th[1];
+	c.lr[0] = th[2];
+	c.lr[1] = th[3];
+	c.si = th[4];
+	c.li[0] = th[5];
+	c.li[1] = th[6];
+	double prod = 1.0;
+	for (int d = 0; d < 2; d++)
+	{
+		const double ss = c.lr[d] * c.lr[d] + c.li[d] * c.li[d];
+		prod *= 2.0 * c.lr[d] * c.li[d] / ss;
+		c.lc[d] = std::sqrt(ss / 2.0);
+	}
+	c.sc = std::sqrt(c.sr * c.si * prod);
+	return c;
+}
+BlockSpec complex_spec(const double* th)
+{
+	const ComplexSub c = complex_sub(th);
+	const double s2 = th[0] * th[0], hn = 0.5 * s2 * th[7] * th[7];
+	BlockSpec s{};
+	s.nb = 2;
+	s.b[0][0] = GaussBlock{s2 * c.sr * c.sr, 1.0 / c.lr[0], 1.0 / c.lr[1], hn};
+	s.b[1][1] = GaussBlock{s2 * c.si * c.si, 1.0 / c.li[0], 1.0 / c.li[1], hn};
+	s.b[0][1] = s.b[1][0] = GaussBlock{s2 * c.sc * c.sc, 1.0 / c.lc[0], 1.0 / c.lc[1], 0.0};
+	return s;
+}
+
+/// Gaussian block of a "purity auxiliary" kernel (kernel.h:285-294): magnitude mag^2 sqrt(lx lp), lengths sqrt(2) l
+GaussBlock aux_block(const double mag, const double lx, const double lp, const double scale)
+{
+	const double m = mag * mag * std::sqrt(lx * lp);
+	return GaussBlock{scale * m * m, 1.0 / (std::sqrt(2.0) * lx), 1.0 / (std::sqrt(2.0) * lp), 0.0};
+}
+/// mixed auxiliary kernel (complex_kernel.cpp:206-219)
+GaussBlock mixed_block(const double ma, const double* la, const double mb, const double* lb, const double scale)
+{
+	double prod = 1.0, l[2];
+	for (int d = 0; d < 2; d++)
+	{
+		prod *= 0.5 * (1.0 / (la[d] * la[d]) + 1.0 / (lb[d] * lb[d]));
+		l[d] = std::sqrt(la[d] * la[d] + lb[d] * lb[d]);
+	}
+	const double m = ma * mb / std::sqrt(std::sqrt(prod));
+	return GaussBlock{scale * m * m, 1.0 / l[0], 1.0 / l[1], 0.0};
+}
+
+double read_scalars(gple_ctx* ctx, const double* d_scal, const int count, double* h)
+{
+	GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_scal, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
+	std::memcpy(h, ctx->h_pinned, count * sizeof(double));
+	return h[0];
+}
+
+constexpr int SCAL_COUNT = 16;
+
+/// Steps shared by both element kinds: build covariance, factorise, invert, solve, column pass.
+/// Returns GPLE_OK or GPLE_ERR_NOT_SPD.
+int train_common(gple_ctx* ctx, gple_model* m, const BlockSpec& spec, const DeviceArray<double>& X, const DeviceArray<double>& y, double* d_scal)
+{
+	const int N = int(m->N), Np = m->Np, n = m->n;
+	GPLE_CUDA(cudaMalloc(&m->X, size_t(2) * Np * sizeof(double)));
+	GPLE_CUDA(cudaMemsetAsync(m->X, 0, size_t(2) * Np * sizeof(double), ctx->stream));
+	GPLE_CUDA(cudaMemcpyAsync(m->X, X.dev, size_t(2) * N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	GPLE_CUDA(cudaMalloc(&m->W, size_t(n) * n * sizeof(double)));
+	GPLE_CUDA(cudaMalloc(&m->v, size_t(n) * sizeof(double)));
+	GPLE_CUDA(cudaMalloc(&m->label, size_t(n) * sizeof(double)));
+	GPLE_CUDA(cudaMalloc(&m->kinv_diag, size_t(3) * n * sizeof(double)));
+	double* K = ctx->ws.get<double>("train.K", size_t(n) * n);
+	int* d_info = ctx->ws.get<int>("train.info", 4);
+	const int tiles = n / 128;
+	GPLE_LAUNCH(ctx, build_cov_lower_kernel, dim3(tiles, tiles), 256, 0, spec, reinterpret_cast<const double2*>(m->X), N, Np, n, K);
+	potrf_trtri(ctx, K, m->W, n, d_info);
+	GPLE_LAUNCH(ctx, label_kernel, 1, 1024, 0, reinterpret_cast<const double2*>(y.dev), N, Np, m->is_complex, m->label, d_scal);
+	double* z = ctx->ws.get<double>("train.z", size_t(n));
+	GPLE_LAUNCH(ctx, trmv_lower_kernel, (n + 7) / 8, 256, 0, m->W, n, m->label, z);
+	const int slabs = std::max(1, std::min(64, n / 512));
+	const int slab = int(round_up(size_t((n + slabs - 1) / slabs), 128));
+	const int nslab = (n + slab - 1) / slab;
+	double* part = ctx->ws.get<double>("train.colpart", size_t(nslab) * 3 * n);
+	GPLE_LAUNCH(ctx, col_pass_kernel, dim3(n / 128, nslab), 128, 0, m->W, n, Np, m->is_complex, z, slab, part);
+	GPLE_LAUNCH(ctx, col_reduce_kernel, (n + 255) / 256, 256, 0, part, n, nslab, m->v, m->kinv_diag, m->is_complex ? m->kinv_diag + n : nullptr);
+	int h_info = 0;
+	GPLE_CUDA(cudaMemcpyAsync(&h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
+	return h_info == 0 ? GPLE_OK : GPLE_ERR_NOT_SPD;
+}
+
+double quadform(gple_ctx* ctx, const gple_model* m, const QuadSpec& qs, const double* w, double* d_out)
+{
+	const int tiles = m->n / 128;
+	double* part = ctx->ws.get<double>("train.quadpart", size_t(tiles) * tiles);
+	GPLE_LAUNCH(ctx, quadform_kernel, dim3(tiles, tiles), 256, 0, qs, reinterpret_cast<const double2*>(m->X), int(m->N), m->Np, w, part);
+	GPLE_LAUNCH(ctx, sum_kernel, 1, 1024, 0, part, tiles * tiles, d_out);
+	double h = 0.0;
+	read_scalars(ctx, d_out, 1, &h);
+	return h;
+}
+
+constexpr int CHUNK_ROWS = 148 * 128;
+
+} // namespace
+
+void gpr_setup_attributes()
+{
+	static bool done = false;
+	if (done)
+	{
+		return;
+	}
+	chol_setup_attributes();
+	GPLE_CUDA(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SMEM_BYTES)));
+	done = true;
+}
+
+void free_model(gple_model* m)
+{
+	if (m == nullptr)
+	{
+		return;
+	}
+	for (double* p : {m->X, m->W, m->v, m->label, m->kinv_diag, m->Kinv, m->dv})
+	{
+		if (p != nullptr)
+		{
+			cudaFree(p);
+		}
+	}
+	delete m;
+}
+
+void ensure_full_inverse(gple_ctx* ctx, gple_model* m)
+{
+	if (m->Kinv != nullptr)
+	{
+		return;
+	}
+	const int n = m->n;
+	GPLE_CUDA(cudaMalloc(&m->Kinv, size_t(n) * n * sizeof(double)));
+	double* U = ctx->ws.get<double>("inv.U", size_t(n) * n);
+	GPLE_LAUNCH(ctx, transpose_kernel, dim3(n / 32, n / 32), dim3(32, 8), 0, m->W, U, n);
+	gemm::GemmArgs g{};
+	g.A = U;
+	g.B = U;
+	g.C = m->Kinv;
+	g.lda = g.ldb = g.ldc = size_t(n);
+	g.M = g.N = g.K = n;
+	g.alpha = 1.0;
+	g.beta = 0.0;
+	g.tri = gemm::A_UPPER | gemm::B_UPPER_NT;
+	gemm_nt(ctx, g);
+}
+
+int train_real(gple_ctx* ctx, const double* X_, const double* y_, size_t N, const double* theta, unsigned flags, gple_model** out_model, gple_real_scalars* out)
+{
+	gpr_setup_attributes();
+	DeviceArray<double> X(ctx, X_, 2 * N, false), y(ctx, y_, 2 * N, false);
+	gple_model* m = new gple_model();
+	m->is_complex = 0;
+	m->N = N;
+	m->Np = int(round_up(N, 128));
+	m->n = m->Np;
+	std::memcpy(m->theta, theta, 4 * sizeof(double));
+	m->flags = flags;
+	m->prior = theta[0] * theta[0] * (1.0 + theta[3] * theta[3]); // kernel.cpp:512 (quirk q3)
+	double* d_scal = ctx->ws.get<double>("train.scal", SCAL_COUNT);
+	int status = GPLE_OK;
+	try
+	{
+		status = train_common(ctx, m, real_spec(theta), X, y, d_scal);
+		GPLE_LAUNCH(ctx, real_scalars_kernel, 1, 1024, 0, reinterpret_cast<const double2*>(m->X), m->label, m->v, m->kinv_diag, int(N), d_scal);
+		double h[SCAL_COUNT];
+		read_scalars(ctx, d_scal, 8, h);
+		m->rescale = h[0];
+		const double nan = std::nan("");
+		gple_real_scalars r{};
+		r.rescale = h[0];
+		r.error = (flags & GPLE_CALC_ERROR) ? h[1] : nan;
+		const double w = h[5] / double(N); // kernel.h:167-179
+		r.magnitude = std::sqrt(std::fabs(w));
+		r.population = r.first_order[0] = r.first_order[1] = r.purity = nan;
+		for (int p = 0; p < 4; p++)
+		{
+			r.d_error[p] = r.d_population[p] = r.d_purity[p] = nan;
+		}
+		if (flags & GPLE_CALC_AVERAGE)
+		{
+			const double f = 2.0 * M_PI * theta[0] * theta[0] * theta[1] * theta[2];
+			r.population = f * h[2] / r.rescale;	   // kernel.cpp:286-297
+			r.first_order[0] = f * h[3] / r.rescale; // kernel.cpp:298-312
+			r.first_order[1] = f * h[4] / r.rescale;
+			QuadSpec qs{};
+			qs.nb = 1;
+			qs.g[0][0][0] = aux_block(theta[0], theta[1], theta[2], 1.0);
+			const double quad = quadform(ctx, m, qs, m->v, d_scal + 8);
+			r.purity = (2.0 * M_PI) * M_PI * quad / (r.rescale * r.rescale); // kernel.cpp:325-335
+		}
+		if (flags & GPLE_CALC_DERIVATIVE)
+		{
+			real_derivatives(ctx, m, flags, h, &r);
+		}
+		if (status == GPLE_ERR_NOT_SPD)
+		{
+			r.error = r.population = r.purity = nan;
+		}
+		if (out != nullptr)
+		{
+			*out = r;
+		}
+	}
+	catch (...)
+	{
+		free_model(m);
+		throw;
+	}
+	*out_model = m;
+	return status;
+}
+
+int train_complex(gple_ctx* ctx, const double* X_, const double* y_, size_t N, const double* theta, unsigned flags, gple_model** out_model, gple_complex_scalars* out)
+{
+	gpr_setup_attributes();
+	DeviceArray<double> X(ctx, X_, 2 * N, false), y(ctx, y_, 2 * N, false);
+	gple_model* m = new gple_model();
+	m->is_complex = 1;
+	m->N = N;
+	m->Np = int(round_up(N, 128));
+	m->n = 2 * m->Np;
+	std::memcpy(m->theta, theta, 8 * sizeof(double));
+	m->flags = flags;
+	m->prior = theta[0] * theta[0] * (theta[1] * theta[1] + theta[4] * theta[4] + theta[7] * theta[7]); // complex_kernel.cpp:632
+	double* d_scal = ctx->ws.get<double>("train.scal", SCAL_COUNT);
+	int status = GPLE_OK;
+	try
+	{
+		status = train_common(ctx, m, complex_spec(theta), X, y, d_scal);
+		GPLE_LAUNCH(ctx, complex_scalars_kernel, 1, 1024, 0, m->label, m->v, m->kinv_diag, m->kinv_diag + m->n, int(N), m->Np, d_scal);
+		double h[SCAL_COUNT];
+		read_scalars(ctx, d_scal, 8, h);
+		m->rescale = h[0];
+		const double nan = std::nan("");
+		gple_complex_scalars r{};
+		r.rescale = h[0];
+		r.error = (flags & GPLE_CALC_ERROR) ? h[1] : nan;
+		r.magnitude = std::sqrt(std::fabs(h[2] / double(N))); // complex_kernel.h:192-204
+		r.purity = nan;
+		for (int p = 0; p < 8; p++)
+		{
+			r.d_error[p] = r.d_purity[p] = nan;
+		}
+		if (flags & GPLE_CALC_AVERAGE)
+		{
+			// complex_kernel.cpp:357-377 with v = (wr + i wi) / 2:
+			//   v^H K1 v + Re v^T K2 v = 1/2 [ wr^T (KR' + KC') wr + wi^T (KI' + KC') wi + 2 wr^T (KRC + KIC) wi ]
+			const ComplexSub c = complex_sub(theta);
+			QuadSpec qs{};
+			qs.nb = 2;
+			qs.g[0][0][0] = aux_block(c.sr, c.lr[0], c.lr[1], 1.0);
+			qs.g[0][0][1] = aux_block(c.sc, c.lc[0], c.lc[1], 1.0);
+			qs.g[1][1][0] = aux_block(c.si, c.li[0], c.li[1], 1.0);
+			qs.g[1][1][1] = aux_block(c.sc, c.lc[0], c.lc[1], 1.0);
+			qs.g[0][1][0] = qs.g[1][0][0] = mixed_block(c.sr, c.lr, c.sc, c.lc, 1.0);
+			qs.g[0][1][1] = qs.g[1][0][1] = mixed_block(c.si, c.li, c.sc, c.lc, 1.0);
+			const double quad = 0.5 * quadform(ctx, m, qs, m->v, d_scal + 8);
+			const double s4 = theta[0] * theta[0] * theta[0] * theta[0];
+			r.purity = (2.0 * M_PI) * 2.0 * M_PI * s4 * quad / (r.rescale * r.rescale);
+		}
+		if (flags & GPLE_CALC_DERIVATIVE)
+		{
+			complex_derivatives(ctx, m, flags, h, &r);
+		}
+		if (status == GPLE_ERR_NOT_SPD)
+		{
+			r.error = r.purity = nan;
+		}
+		if (out != nullptr)
+		{
+			*out = r;
+		}
+	}
+	catch (...)
+	{
+		free_model(m);
+		throw;
+	}
+	*out_model = m;
+	return status;
+}
+
+/// Batched prediction of `Q` points on the device.  d_pred / d_cut hold nb doubles per point.
+void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size_t Q, const double* d_yq, double* d_pred, double* d_var, double* d_cut, double* d_err)
+{
+	gpr_setup_attributes();
+	const int nb = m->is_complex ? 2 : 1;
+	const BlockSpec spec = m->is_complex ? complex_spec(m->theta) : real_spec(m->theta);
+	const long long total_rows = (long long)(Q)*nb;
+	const int n = m->n;
+	const int max_rows = int(std::min<long long>(CHUNK_ROWS, (long long)round_up(size_t(total_rows), 128)));
+	double* A = ctx->ws.get<double>("pred.A", size_t(max_rows) * n);
+	double* pred = ctx->ws.get<double>("pred.f", size_t(max_rows));
+	double* q = ctx->ws.get<double>("pred.q", size_t(max_rows));
+	if (d_err != nullptr)
+	{
+		GPLE_CUDA(cudaMemsetAsync(d_err, 0, sizeof(double), ctx->stream));
+	}
+	for (long long row0 = 0; row0 < total_rows; row0 += CHUNK_ROWS)
+	{
+		const int rows_real = int(std::min<long long>(CHUNK_ROWS, total_rows - row0));
+		const int rows = int(round_up(size_t(rows_real), 128));
+		GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, reinterpret_cast<const double2*>(d_Xq), (long long)Q, row0, rows, reinterpret_cast<const double2*>(m->X), int(m->N), m->Np, n, m->v, A, pred);
+		if (d_var != nullptr || d_cut != nullptr)
+		{
+			GPLE_LAUNCH(ctx, var_gemm_kernel, rows / 128, gemm::THREADS, gemm::SMEM_BYTES, A, m->W, n, q);
+		}
+		else
+		{
+			GPLE_CUDA(cudaMemsetAsync(q, 0, size_t(rows) * sizeof(double), ctx->stream));
+		}
+		if (m->is_complex)
+		{
+			GPLE_LAUNCH(ctx, finalize_complex_kernel, (rows / 2 + 255) / 256, 256, 0, pred, q, rows, row0, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
+		}
+		else
+		{
+			GPLE_LAUNCH(ctx, finalize_real_kernel, (rows + 255) / 256, 256, 0, pred, q, rows, row0, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
+		}
+		if (d_err != nullptr && d_yq != nullptr)
+		{
+			GPLE_LAUNCH(ctx, sqerr_kernel, 1, 1024, 0, pred, rows, row0, total_rows, d_yq, nb, nb, m->rescale, d_err);
+		}
+	}
+}
+
+void kernel_real_device(gple_ctx* ctx, const double* XL, int nL, const double* XR, int nR, const double* th, int same, double* K, double* dK)
+{
+	GPLE_LAUNCH(ctx, kernel_real_kernel, dim3((nL + 255) / 256, nR), 256, 0, reinterpret_cast<const double2*>(XL), nL, reinterpret_cast<const double2*>(XR), nR, th[0], th[1], th[2], th[3], same, K, dK);
+}
+
+void kernel_complex_device(gple_ctx* ctx, const double* XL, int nL, const double* XR, int nR, const double* th, int same, double* K, double* Kt)
+{
+	const ComplexSub c = complex_sub(th);
+	const GaussBlock gr{c.sr * c.sr, 1.0 / c.lr[0], 1.0 / c.lr[1], 0.0}, gi{c.si * c.si, 1.0 / c.li[0], 1.0 / c.li[1], 0.0}, gc{c.sc * c.sc, 1.0 / c.lc[0], 1.0 / c.lc[1], 0.0};
+	GPLE_LAUNCH(ctx, kernel_complex_kernel, dim3((nL + 255) / 256, nR), 256, 0, reinterpret_cast<const double2*>(XL), nL, reinterpret_cast<const double2*>(XR), nR, gr, gi, gc, th[0] * th[0], th[7] * th[7], same, K, reinterpret_cast<double2*>(Kt));
+}
+
+} // namespace gple

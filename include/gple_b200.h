@@ -1,0 +1,165 @@
+/* gple_b200.h -- C-ABI of the B200-native GPR-MQCLE hot path.
+ *
+ * The reference (kaigu1997/gaussian_process_liouville_equation, directory
+ * gaussian_process_liouville_equation/ = "gple/") has no FFI layer: its hot path sits behind ordinary
+ * C++ headers.  Each entry point below replaces the work done behind one of those interfaces and is
+ * what the reference-side shim binds.  Conventions:
+ *   - every function returns an int status (GPLE_OK or an error code); no C++ exceptions cross;
+ *   - array arguments may be HOST or DEVICE pointers (detected with cudaPointerGetAttributes);
+ *     host inputs are copied to the device on entry, host outputs copied back before return;
+ *   - phase-space coordinates are interleaved (x, p) pairs = the reference's `PhasePoints`
+ *     (Eigen::Matrix<double, 2, Dynamic>, column-major; gple/stdafx.h:153);
+ *   - complex numbers are interleaved (re, im) pairs = std::complex<double>;
+ *   - matrices returned to the caller are column-major like Eigen::MatrixXd;
+ *   - evolved points are the 32-byte AoS `PhaseSpacePoint` {x, p, Re rho, Im rho} (gple/storage.h:232-297);
+ *   - non-finite scalars are returned as they are: the host shim applies `make_normal` (gple/opt.cpp:420-431).
+ * A context is bound to one CUDA device and one stream; calls on one context are serialised by the caller.
+ */
+#ifndef GPLE_B200_H
+#define GPLE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+	typedef struct gple_ctx gple_ctx;
+	typedef struct gple_model gple_model; /* one trained density-matrix element (real or complex kernel) */
+
+	enum gple_status
+	{
+		GPLE_OK = 0,
+		GPLE_ERR_ARG = 1,	  /* bad argument (null pointer, zero size, wrong model kind) */
+		GPLE_ERR_NOT_SPD = 2, /* factorisation met a non-positive pivot; scalars are NaN */
+		GPLE_ERR_CUDA = 3,	  /* CUDA runtime failure, see gple_last_error */
+		GPLE_ERR_STATE = 4	  /* quantity was not computed for this model (flag missing) */
+	};
+
+	/* flags of gple_train_*: the three booleans of TrainingKernel's constructor (gple/kernel.h:128-134) */
+	enum gple_train_flags
+	{
+		GPLE_CALC_ERROR = 1,
+		GPLE_CALC_AVERAGE = 2,
+		GPLE_CALC_DERIVATIVE = 4
+	};
+
+	/* Tully models (gple/pes.h:28-36); the reference selects one at compile time (pes.h:38-41) */
+	enum gple_pes_model
+	{
+		GPLE_SAC = 0,
+		GPLE_DAC = 1,
+		GPLE_ECR = 2
+	};
+
+	/* ---- context -------------------------------------------------------------------------------- */
+	int gple_ctx_create(int device, gple_ctx** ctx);
+	int gple_ctx_destroy(gple_ctx* ctx);
+	/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
+	int gple_ctx_set_stream(gple_ctx* ctx, void* cuda_stream);
+	int gple_ctx_sync(gple_ctx* ctx);
+	const char* gple_last_error(const gple_ctx* ctx);
+	/* Number of CUDA kernels this context has launched since creation (bench.py's `gpu_launches`). */
+	unsigned long long gple_launch_count(const gple_ctx* ctx);
+	const char* gple_version(void);
+
+	/* ---- kernel matrices ---------------------------------------------------------------------------
+	 * Replaces KernelBase::KernelBase + delta_kernel (gple/kernel.cpp:8-31,217-242) and calculate_derivative
+	 * (kernel.cpp:168-215).  theta = (sigma_f, l_x, l_p, sigma_n) (gple/kernel.h:33,41).  same_set != 0 is the
+	 * reference's `LeftFeature.data() == RightFeature.data()` (training-set) case.
+	 * K_out: nL x nR; dK_out (may be NULL): 4 matrices nL x nR, one per parameter. */
+	int gple_kernel_real(gple_ctx* ctx, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[4], int same_set, double* K_out, double* dK_out);
+	/* Replaces ComplexKernelBase::ComplexKernelBase (gple/complex_kernel.cpp:134-200).
+	 * theta = (sigma, sigma_R, l_Rx, l_Rp, sigma_I, l_Ix, l_Ip, sigma_n) (complex_kernel.cpp:230-256).
+	 * K_out: nL x nR real; Kt_out: nL x nR complex (pseudo-covariance). */
+	int gple_kernel_complex(gple_ctx* ctx, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[8], int same_set, double* K_out, double* Kt_out);
+
+	/* ---- training ----------------------------------------------------------------------------------
+	 * Replaces TrainingKernel::TrainingKernel (gple/kernel.cpp:244-479) and its getters (kernel.h:136-243).
+	 * X: N points; y: N complex labels (imaginary part ignored, kernel.cpp:279-280). */
+	typedef struct gple_real_scalars
+	{
+		double rescale;		   /* get_rescale_factor()  kernel.cpp:279 */
+		double error;		   /* get_error()           kernel.cpp:285 (LOOCV squared error) */
+		double population;	   /* get_population()      kernel.cpp:286-297 */
+		double first_order[2]; /* get_1st_order_average() kernel.cpp:298-312 */
+		double purity;		   /* get_purity()          kernel.cpp:325-335 */
+		double magnitude;	   /* get_magnitude()       kernel.h:167-179 */
+		double d_error[4];	   /* get_error_derivative()      kernel.cpp:381-400 */
+		double d_population[4]; /* get_population_derivative() kernel.cpp:401-435 */
+		double d_purity[4];	   /* get_purity_derivative()     kernel.cpp:436-477 */
+	} gple_real_scalars;
+	int gple_train_real(gple_ctx* ctx, const double* X, const double* y, size_t N, const double theta[4], unsigned flags, gple_model** model, gple_real_scalars* out);
+
+	/* Replaces TrainingComplexKernel::TrainingComplexKernel (gple/complex_kernel.cpp:221-592). */
+	typedef struct gple_complex_scalars
+	{
+		double rescale;		/* complex_kernel.cpp:262 */
+		double error;		/* complex_kernel.cpp:270-286 */
+		double purity;		/* complex_kernel.cpp:357-377 */
+		double magnitude;	/* complex_kernel.h:192-204 */
+		double d_error[8];	/* complex_kernel.cpp:444-474 */
+		double d_purity[8]; /* complex_kernel.cpp:475-590 */
+	} gple_complex_scalars;
+	int gple_train_complex(gple_ctx* ctx, const double* X, const double* y, size_t N, const double theta[8], unsigned flags, gple_model** model, gple_complex_scalars* out);
+
+	/* Matrix / vector getters of a trained element.  `which`: */
+	enum gple_model_field
+	{
+		GPLE_FIELD_INVERSE = 1,		  /* real: get_inverse() N x N (kernel.h:153) */
+		GPLE_FIELD_INV_LABEL = 2,	  /* real: get_inverse_times_label() N; complex: upper part of augmented inverse label, N complex */
+		GPLE_FIELD_LABEL = 3,		  /* rescaled label, N real / N complex */
+		GPLE_FIELD_UPPER_LEFT = 4,	  /* complex: get_upper_left_block_of_augmented_inverse()  N x N complex (complex_kernel.h:208) */
+		GPLE_FIELD_LOWER_LEFT = 5,	  /* complex: get_lower_left_block_of_augmented_inverse()  N x N complex (complex_kernel.h:215) */
+		GPLE_FIELD_INV_LABEL_DERIV = 8 /* + parameter index: derivative of INV_LABEL over that parameter */
+	};
+	int gple_model_get(gple_ctx* ctx, const gple_model* model, int which, double* out);
+	int gple_model_is_complex(const gple_model* model);
+	size_t gple_model_size(const gple_model* model);
+	int gple_model_destroy(gple_ctx* ctx, gple_model* model);
+
+	/* ---- batched prediction --------------------------------------------------------------------------
+	 * Replaces PredictiveKernel::PredictiveKernel (gple/kernel.cpp:481-544): raw prediction K* v (:495),
+	 * variance k** - k K^-1 k^T (:496-518), cutoff prediction (:519, kernel.h:301-332) and, when yq != NULL,
+	 * the squared validation error (:522) plus (if the model was trained with GPLE_CALC_DERIVATIVE and
+	 * derr_out != NULL) its parameter gradient (:524-541).  Any output pointer may be NULL. */
+	int gple_predict_real(gple_ctx* ctx, const gple_model* model, const double* Xq, size_t Q, const double* yq, double* pred_out, double* var_out, double* cutoff_out, double* err_out, double* derr_out);
+	/* Replaces PredictiveComplexKernel::PredictiveComplexKernel (gple/complex_kernel.cpp:594-670).
+	 * yq, pred_out, cutoff_out are complex (interleaved); var_out is real. */
+	int gple_predict_complex(gple_ctx* ctx, const gple_model* model, const double* Xq, size_t Q, const double* yq, double* pred_out, double* var_out, double* cutoff_out, double* err_out, double* derr_out);
+
+	/* Replaces loose_function (gple/opt.cpp:441-482): LOOCV error of the training set + squared error on the
+	 * extra set (+ gradient when grad != NULL).  nparam = 4 (real kernel) or 8 (complex kernel).  The value is
+	 * returned un-clamped; the caller applies make_normal. */
+	int gple_loose_function(gple_ctx* ctx, const double* x, int nparam, double* grad, const double* X, const double* y, size_t N, const double* Xe, const double* ye, size_t M, double* value);
+
+	/* ---- dynamics ------------------------------------------------------------------------------------
+	 * Replaces adiabatic_potential / adiabatic_force / adiabatic_coupling (gple/pes.cpp:127-189) for n positions:
+	 * E: 2 per point (E_0, E_1); F: 3 per point (F_00, F_10, F_11); D: 1 per point (d_10 = -d_01). */
+	int gple_pes(gple_ctx* ctx, int pes_model, const double* x, size_t n, double* E, double* F, double* D);
+
+	/* Replaces evolve() (gple/evolve.cpp:377-423) with the GPR-backed `predict_distribution` of
+	 * gple/main.cpp:75-101 as the DistributionFunction: all points of the three elements
+	 * (lower-triangular order rho00, rho10, rho11) are moved forward by dt and their densities are rebuilt
+	 * from the 9 backward-propagated predictions per point (evolve.cpp:184-372).  A NULL model means the
+	 * element has no predictor (predicts 0, main.cpp:85-99).  Points are updated in place. */
+	int gple_evolve(gple_ctx* ctx, int pes_model, const gple_model* m00, const gple_model* m10, const gple_model* m11, double* pts00, size_t n00, double* pts10, size_t n10, double* pts11, size_t n11, double mass, double dt);
+
+	/* Replaces new_point_predict() (gple/evolve.cpp:425-443) for n phase points r of element (row, col):
+	 * out = n complex densities. */
+	int gple_new_point_predict(gple_ctx* ctx, int pes_model, const gple_model* m00, const gple_model* m10, const gple_model* m11, const double* r, size_t n, int row, int col, double mass, double dt, double* out);
+
+	/* Replaces the transform_reduce observables of gple/predict.cpp:43-244 for one element.
+	 * out[9] = sum Re rho, sum x Re rho, sum p Re rho, sum x, sum p, sum x^2, sum p^2,
+	 *          sum (p^2/2m + E_pes(x)) Re rho, sum |rho|^2. */
+	int gple_observables(gple_ctx* ctx, int pes_model, const double* pts, size_t n, double mass, int pes_index, double out[9]);
+
+	/* ---- measurement helpers (bench.py) --------------------------------------------------------------- */
+	/* Register-resident DMMA / DFMA loops: measured FP64 tensor and vector peaks of this GPU, in TFLOP/s. */
+	int gple_measure_fp64_peak(gple_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPLE_B200_H */

@@ -1,0 +1,71 @@
+"""GPU parity of the complex (widely-linear) kernel chain against the CPU oracle through the C-ABI.
+The CUDA path evaluates the equivalent real process over [Re f; Im f]; the oracle keeps the
+reference's formulation (complex LDLT, K^-1 conj(Kt), P, Q).  Tolerances as in test_gpu_real.py."""
+import numpy as np
+import pytest
+
+from gaussian_process_liouville_equation_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+THETA = np.array([1.0, 1.2, 0.8 * syn.SIGMA_X, 1.1 * syn.SIGMA_P, 0.7, 1.1 * syn.SIGMA_X, 0.9 * syn.SIGMA_P, 2e-2])
+
+
+@pytest.fixture(scope="module")
+def ck():
+    from gaussian_process_liouville_equation_b200 import complex_kernel
+
+    return complex_kernel
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def test_kernel_matrices_parity(ck, oracle):
+    X, _ = syn.training_set(1, 1, 130)
+    Xq, _ = syn.training_set(2, 1, 77)
+    for XL, XR, same in ((X, X, True), (Xq, X, False)):
+        K, Kt = ck.kernel_matrices(XL, XR, THETA, same)
+        Ko, Kto = oracle.kernel_complex(XL, XR, THETA, same, False)
+        assert (np.abs(K - Ko) <= 1e-12 * np.abs(Ko) + 1e-300).all()
+        assert (np.abs(Kt - Kto) <= 1e-12 * np.abs(Kto) + 1e-300).all()
+
+
+@pytest.mark.parametrize("n,theta", [(48, THETA), (200, THETA), (150, syn.theta_complex())])
+def test_training_parity(ck, oracle, n, theta):
+    X, y = syn.training_set(1, 1, n)
+    k = ck.TrainingComplexKernel(theta, (X, y), True, True, False)
+    o = oracle.TrainingComplexKernel(theta, X, y, True, True, False)
+    assert k.status == 0
+    assert k.get_rescale_factor() == pytest.approx(o.rescale, rel=1e-15)
+    assert k.get_error() == pytest.approx(o.error, rel=1e-8)
+    assert k.get_purity() == pytest.approx(o.purity, rel=1e-9)
+    assert k.get_magnitude() == pytest.approx(o.magnitude, rel=1e-9)
+    assert rel(k.get_upper_part_of_augmented_inverse_times_label(), o.v) <= 1e-8
+    assert rel(k.get_label(), o.label) <= 1e-15
+    if n <= 64:
+        sc = np.abs(o.P).max()
+        assert np.abs(k.get_upper_left_block_of_augmented_inverse() - o.P).max() <= 1e-8 * sc
+        assert np.abs(k.get_lower_left_block_of_augmented_inverse() - o.Q).max() <= 1e-8 * sc
+
+
+def test_prediction_parity(ck, oracle):
+    X, y = syn.training_set(1, 1, 200)
+    Xq, _ = syn.extra_points(1, 1, X, 700)
+    Xq[:60] += np.array([4.0, 0.0])
+    Xq[60:160] += np.array([1.8, 0.0])
+    yq = syn.labels(1, Xq, (0.0, syn.P0))
+    k = ck.TrainingComplexKernel(THETA, (X, y), True, False, False)
+    o = oracle.TrainingComplexKernel(THETA, X, y, True, False, False)
+    p = ck.PredictiveComplexKernel(Xq, k, False, yq)
+    r = o.predict(Xq, yq, False)
+    prior = THETA[0] ** 2 * (THETA[1] ** 2 + THETA[4] ** 2 + THETA[7] ** 2)
+    assert rel(p.get_prediction(), r["pred"]) <= 1e-8
+    assert np.abs(p.get_variance() - r["var"]).max() <= 1e-8 * prior
+    assert p.get_error() == pytest.approx(r["error"], rel=1e-8)
+    gate_o = np.abs(r["cutoff"] * o.rescale) / np.maximum(np.abs(r["pred"]), 1e-300)
+    sharp = (gate_o < 1e-15) | (np.abs(gate_o - 1) < 1e-15)
+    scale = np.abs(r["cutoff"]).max()
+    assert np.abs(p.get_cutoff_prediction() - r["cutoff"])[sharp].max() <= 1e-8 * scale
+    assert np.abs(p.get_cutoff_prediction() - r["cutoff"]).max() <= 1e-5 * scale

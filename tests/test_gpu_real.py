@@ -1,0 +1,156 @@
+"""GPU parity of the real-kernel chain against the CPU oracle, through the C-ABI (via the host mirror).
+
+Tolerances are BASELINE.json's: kernel matrices 1e-12 relative, predictions / losses 1e-9 relative.
+"Relative" for vectors means relative to the largest magnitude of the vector (the quantities are sums of
+O(N) terms of that size).  The variance k** - k K^-1 k^T is a difference of nearly equal numbers in the
+reference's own formulation (two summation orders of the ORACLE differ by ~1e-11 k**, see
+tests/test_oracle_real.py), so it is compared relative to the prior variance k**.
+"""
+import numpy as np
+import pytest
+
+from gaussian_process_liouville_equation_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gk():
+    from gaussian_process_liouville_equation_b200 import kernel
+
+    return kernel
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (50, 31), (300, 257)])
+def test_kernel_matrix_parity(gk, oracle, n, m):
+    X, _ = syn.training_set(1, 0, n)
+    Xq, _ = syn.training_set(2, 0, m)
+    if n > 7 and m > 3:
+        Xq[3] = X[7]
+    th = np.array([1.3, 0.6, 0.9, 0.05])
+    for XL, XR, same in ((X, X, True), (Xq, X, False)):
+        K, dK = gk.kernel_matrix(XL, XR, th, same, True)
+        Ko, dKo = oracle.kernel_real(XL, XR, th, same, True)
+        assert np.abs(K - Ko).max() <= 1e-12 * np.abs(Ko).max()
+        assert (np.abs(K - Ko) <= 1e-12 * np.abs(Ko) + 1e-300).all()  # elementwise relative
+        for p in range(4):
+            assert (np.abs(dK[p] - dKo[p]) <= 1e-12 * np.abs(dKo[p]) + 1e-300).all()
+
+
+@pytest.mark.parametrize("n", [1, 96, 300, 700])
+def test_training_scalars_parity(gk, oracle, n):
+    X, y = syn.training_set(1, 0, n)
+    th = syn.theta_real()
+    k = gk.TrainingKernel(th, (X, y), True, True, False)
+    o = oracle.TrainingKernel(th, X, y, True, True, False)
+    assert k.status == 0
+    assert k.get_rescale_factor() == pytest.approx(o.rescale, rel=1e-15)
+    assert k.get_error() == pytest.approx(o.error, rel=1e-9)
+    assert k.get_population() == pytest.approx(o.population, rel=1e-9)
+    assert k.get_1st_order_average() == pytest.approx(o.first_order, rel=1e-9, abs=1e-9 * abs(o.first_order).max())
+    assert k.get_purity() == pytest.approx(o.purity, rel=1e-9)
+    assert k.get_magnitude() == pytest.approx(o.magnitude, rel=1e-9)
+    assert rel(k.get_inverse_times_label(), o.v) <= 1e-9
+    assert rel(k.get_label(), o.label) <= 1e-15
+    if n <= 300:
+        assert rel(k.get_inverse(), o.inverse) <= 1e-9
+
+
+def test_prediction_parity(gk, oracle):
+    X, y = syn.training_set(1, 0, 300)
+    th = syn.theta_real()
+    Xq, _ = syn.extra_points(1, 0, X, 1500)
+    Xq[:100] += np.array([4.0, 0.0])
+    Xq[100:300] += np.array([1.7, 0.0])
+    Xq[300] = X[5]  # exact coincidence: delta_kernel adds the noise term (kernel.cpp:16-29)
+    yq = syn.labels(0, Xq, (0.0, syn.P0)).real
+    k = gk.TrainingKernel(th, (X, y), True, True, False)
+    o = oracle.TrainingKernel(th, X, y, True, True, False)
+    p = gk.PredictiveKernel(Xq, k, False, yq)
+    r = o.predict(Xq, yq, False)
+    prior = th[0] ** 2 * (1 + th[3] ** 2)
+    assert rel(p.get_prediction(), r["pred"]) <= 1e-9
+    assert np.abs(p.get_variance() - r["var"]).max() <= 1e-9 * prior
+    assert p.get_error() == pytest.approx(r["error"], rel=1e-9)
+    # cutoff prediction: gate closed / open -> exact; inside the cubic band the gate inherits the variance noise
+    gate_o = np.divide(r["cutoff"] * o.rescale, r["pred"], out=np.ones_like(r["pred"]), where=r["pred"] != 0)
+    sharp = (gate_o == 0) | (gate_o == 1)
+    assert sharp.any() and (~sharp).any()
+    scale = np.abs(r["cutoff"]).max()
+    near_edge = np.abs(r["pred"] ** 2 - r["var"]) < 1e-6 * r["var"]  # a gate flip here is rounding, not error
+    ok = sharp & ~near_edge
+    assert np.abs(p.get_cutoff_prediction() - r["cutoff"])[ok].max() <= 1e-9 * scale
+    assert np.abs(p.get_cutoff_prediction() - r["cutoff"]).max() <= 1e-6 * scale
+
+
+def test_single_point_prediction_like_predict_distribution(gk, oracle):
+    """main.cpp:75-101: PredictiveKernel(r, kernel, false).get_cutoff_prediction().value() for one point."""
+    X, y = syn.training_set(3, 0, 200)
+    th = syn.theta_real()
+    k = gk.TrainingKernel(th, (X, y))
+    o = oracle.TrainingKernel(th, X, y)
+    for r in (X[17] + 0.01, np.array([0.3, syn.P0 - 0.2])):
+        a = gk.PredictiveKernel(r, k).get_cutoff_prediction()
+        b = o.predict(r.reshape(1, 2))["cutoff"]
+        assert a == pytest.approx(b, rel=1e-9)
+
+
+def test_gradients_parity(gk, oracle):
+    X, y = syn.training_set(5, 0, 200)
+    th = np.array([1.0, 0.9 * syn.SIGMA_X, 1.1 * syn.SIGMA_P, 2e-2])
+    k = gk.TrainingKernel(th, (X, y), True, True, True)
+    o = oracle.TrainingKernel(th, X, y, True, True, True)
+    sc = np.abs(o.derror).max()
+    assert np.abs(k.get_error_derivative() - o.derror).max() <= 1e-8 * sc
+    assert np.abs(k.get_population_derivative() - o.dpopulation).max() <= 1e-9 * np.abs(o.dpopulation).max()
+    assert np.abs(k.get_purity_derivative() - o.dpurity).max() <= 1e-9 * np.abs(o.dpurity).max()
+    dv = k.get_inverse_times_label_derivative()
+    for p in range(4):
+        assert np.abs(dv[p] - o.dv(p)).max() <= 1e-8 * np.abs(o.dv(p)).max()
+    # validation error gradient (quirk q1) and loose_function (opt.cpp:441-482)
+    Xq, yq = syn.extra_points(5, 0, X, 1000)
+    pq = gk.PredictiveKernel(Xq, k, True, yq.real)
+    ro = o.predict(Xq, yq.real, True)
+    assert pq.get_error() == pytest.approx(ro["error"], rel=1e-9)
+    assert np.abs(pq.get_error_derivative() - ro["derror"]).max() <= 1e-7 * np.abs(ro["derror"]).max()
+    from gaussian_process_liouville_equation_b200 import dynamics
+
+    val, g = dynamics.loose_function(th, (X, y), (Xq, yq), grad=True)
+    vo, go = oracle.loose_function(th, X, y, Xq, yq, grad=True)
+    assert val == pytest.approx(vo, rel=1e-9)
+    assert np.abs(g - go).max() <= 1e-7 * np.abs(go).max()
+    assert dynamics.loose_function(th, (X, y), (Xq, yq)) == pytest.approx(vo, rel=1e-9)
+
+
+def test_large_n_properties(gk):
+    """N = 2048 (BASELINE config C2): size-independent properties instead of the (slow) oracle."""
+    n = 2048
+    X, y = syn.training_set(2, 0, n)
+    th = syn.theta_real()
+    k = gk.TrainingKernel(th, (X, y), True, True, False)
+    assert k.status == 0
+    v, lab = k.get_inverse_times_label(), k.get_label()
+    K = gk.kernel_matrix(X, X, th, True)
+    assert np.abs(K @ v - lab).max() <= 1e-8 * np.abs(lab).max()  # K (K^-1 y) = y
+    assert k.get_population() == pytest.approx(0.6, rel=1e-3)
+    assert k.get_purity() == pytest.approx(0.36, rel=2e-3)
+    # linearity in the labels: v(2y) has the same rescaled solution, population doubles
+    k2 = gk.TrainingKernel(th, (X, 2 * y), True, True, False)
+    assert k2.get_population() == pytest.approx(2 * k.get_population(), rel=1e-10)
+    # prediction at training points reproduces label - sigma_n^2-weighted residual: K* v with K* = K - sigma^2 I
+    p = gk.PredictiveKernel(X[:512] + 1e-9, k)
+    expect = (K[:512] - th[0] ** 2 * th[3] ** 2 * np.eye(n)[:512]) @ v
+    assert np.abs(p.get_prediction() - expect).max() <= 1e-7 * np.abs(expect).max()
+    assert (p.get_variance() > 0).all() and (p.get_variance() < th[0] ** 2 * (1 + th[3] ** 2)).all()
+
+
+def test_not_spd_is_reported(gk):
+    """Duplicate points with zero noise make K singular: status code, NaN scalars, no exception."""
+    X, y = syn.training_set(1, 0, 64)
+    X[1] = X[0]
+    k = gk.TrainingKernel(np.array([1.0, 0.7, 0.7, 0.0]), (X, y), True, True, False)
+    assert k.status == 2 and np.isnan(k.get_error())
