@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- one GPR-MQCLE time step per "step" on synthetic Tully-model inputs (BASELINE.json configs[1]).
+
+Workload C2: Tully simple avoided crossing, N = 2048 training points per density-matrix element,
+all three elements (rho00, rho10, rho11) populated (mid-crossing snapshot), Q = 1e5 evolved Monte-Carlo
+phase-space points per element per step.  One step = what gple/main.cpp:135-188 does on a tick without
+re-optimisation:
+    TrainingKernels(params, density)   (kernel build + factorise + inverse + LOOCV error + averages, 3 elements)
+  + evolve(points)                     (forward move, 9 back-propagated GPR predictions per point, recombination)
+With 3 elements every element predictor answers 8 Q queries per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 (torchrun, one rank per GPU): the evolved points are block-partitioned over the ranks (strong scaling,
+total work fixed), every rank rebuilds the three element models redundantly, and the only collective is the
+NCCL all-gather of the evolved point sets at the end of the step (BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from gaussian_process_liouville_equation_b200 import synthetic as syn  # noqa: E402
+
+N_TRAIN = 2048
+Q_POINTS = 100_000
+PES_MODEL = 0  # SAC
+CENTRE = (0.0, syn.P0)
+THETA_R = syn.theta_real()
+THETA_C = np.array([1.0, 1.2, 0.8 * syn.SIGMA_X, 1.1 * syn.SIGMA_P, 0.7, 1.1 * syn.SIGMA_X, 0.9 * syn.SIGMA_P, syn.INITIAL_NOISE])
+METRIC = "gpr_mqcle_time_steps_per_s"
+UNIT = "steps/s"
+WORKLOAD = ("C2: Tully SAC, N=2048 training points/element, 3 elements (rho00,rho10,rho11), Q=1e5 evolved MC points/element/step; "
+            "step = TrainingKernels rebuild (3 elements) + evolve (8Q GPR predictions per element)")
+
+
+def make_inputs():
+    sets = [syn.training_set(2, e, N_TRAIN, CENTRE) for e in range(3)]
+    pts = []
+    for e in range(3):
+        Xe, ye = syn.extra_points(2, e, sets[e][0], Q_POINTS, CENTRE)
+        pts.append(syn.points_aos(Xe, ye))
+    return sets, pts
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference timed on the host cores, bounded sample
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_sample(sets):
+    """One bounded sample of the C2 step on the CPU (oracle = port of the reference's Eigen/CPU implementation).
+
+    Measured: real-element TrainingKernel at N=2048; 128 real single-model predictions at N=2048;
+    TrainingComplexKernel at N=1024 (x8 for the N^3 scaling to 2048); 32 complex predictions at N=1024 (x4, N^2).
+    Returns (seconds per full step, description).
+    """
+    from oracle import oracle as orc
+
+    t = time.perf_counter()
+    k0 = orc.TrainingKernel(THETA_R, sets[0][0], sets[0][1], True, True, False)
+    t_train_real = time.perf_counter() - t
+    Xq, _ = syn.extra_points(3, 0, sets[0][0], 128, CENTRE)
+    t = time.perf_counter()
+    k0.predict(Xq)
+    t_q_real = (time.perf_counter() - t) / len(Xq)
+    nc = 1024
+    t = time.perf_counter()
+    k1 = orc.TrainingComplexKernel(THETA_C, sets[1][0][:nc], sets[1][1][:nc], True, True, False)
+    t_train_cplx = (time.perf_counter() - t) * (N_TRAIN / nc) ** 3
+    Xq, _ = syn.extra_points(3, 1, sets[1][0], 32, CENTRE)
+    t = time.perf_counter()
+    k1.predict(Xq)
+    t_q_cplx = (time.perf_counter() - t) / len(Xq) * (N_TRAIN / nc) ** 2
+    queries = 8 * Q_POINTS
+    step_s = 2 * t_train_real + t_train_cplx + 2 * queries * t_q_real + queries * t_q_cplx
+    desc = (f"oracle port, {orc.num_threads()} threads: real train N=2048 measured ({t_train_real:.2f}s), 128 real queries N=2048 "
+            f"({t_q_real * 1e3:.2f} ms/query), complex train N=1024 x8 ({t_train_cplx:.1f}s), 32 complex queries N=1024 x4 "
+            f"({t_q_cplx * 1e3:.2f} ms/query); step = 2 real + 1 complex train + 8Q queries per predictor, extrapolated")
+    return step_s, desc, orc.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sets = [syn.training_set(2, e, N_TRAIN, CENTRE) for e in range(3)]
+    times, desc, cores = [], "", 1
+    for i in range(args.warmup + args.steps):
+        s, desc, cores = cpu_sample(sets)
+        if i >= args.warmup:
+            times.append(s)
+    step_s = float(np.mean(times))
+    value = 1.0 / step_s
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference cannot be compiled here (Eigen/NLopt/xtensor/MKL/TBB absent); CPU restatement timed"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) == 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": reasons}
+
+
+def run_ours(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from gaussian_process_liouville_equation_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = L.Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    lib = ctx.lib
+
+    sets, pts_all = make_inputs()
+    # block partition of the evolved points (strong scaling); every rank keeps the full training sets
+    lo, hi = Q_POINTS * rank // world, Q_POINTS * (rank + 1) // world
+    nloc = hi - lo
+    thetas = [THETA_R, THETA_C, THETA_R]
+    d_X = [torch.from_numpy(s[0]).to(dev) for s in sets]
+    d_y = [torch.from_numpy(np.ascontiguousarray(s[1]).view(np.float64)).to(dev) for s in sets]
+    d_pts0 = [torch.from_numpy(p[lo:hi].copy()).to(dev) for p in pts_all]
+    d_pts = [t.clone() for t in d_pts0]
+    d_gather = [torch.empty((Q_POINTS, 4), dtype=torch.float64, device=dev) for _ in range(3)] if world > 1 else None
+    h_X = [torch.from_numpy(s[0]).pin_memory() for s in sets]
+    h_y = [torch.from_numpy(np.ascontiguousarray(s[1]).view(np.float64)).pin_memory() for s in sets]
+    h_pts0 = [torch.from_numpy(p[lo:hi].copy()).pin_memory() for p in pts_all]
+    h_pts = [t.clone().pin_memory() for t in h_pts0]
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    last_scalars = {}
+
+    def train_all(X, y):
+        models = []
+        for e in range(3):
+            h = C.c_void_p()
+            th = np.ascontiguousarray(thetas[e])
+            if e == 1:
+                s = L.ComplexScalars()
+                ctx.check(lib.gple_train_complex(ctx.h, X[e].data_ptr(), y[e].data_ptr(), N_TRAIN, L.addr(th), L.CALC_ERROR | L.CALC_AVERAGE, C.byref(h), C.byref(s)))
+                last_scalars["purity10"], last_scalars["error10"] = s.purity, s.error
+            else:
+                s = L.RealScalars()
+                ctx.check(lib.gple_train_real(ctx.h, X[e].data_ptr(), y[e].data_ptr(), N_TRAIN, L.addr(th), L.CALC_ERROR | L.CALC_AVERAGE, C.byref(h), C.byref(s)))
+                last_scalars[f"population{e}"] = s.population
+            models.append(h)
+        return models
+
+    def step(X, y, pts):
+        """One time step through the C-ABI.  X, y, pts: device tensors (resident run) or pinned host tensors (e2e run)."""
+        models = train_all(X, y)
+        ctx.check(lib.gple_evolve(ctx.h, PES_MODEL, models[0], models[1], models[2], pts[0].data_ptr(), nloc, pts[1].data_ptr(), nloc, pts[2].data_ptr(), nloc, syn.MASS, syn.DT))
+        for h in models:
+            lib.gple_model_destroy(ctx.h, h)
+        if world > 1 and pts[0].is_cuda:
+            for e in range(3):
+                dist.all_gather_into_tensor(d_gather[e], pts[e])
+
+    def reset():
+        for a, b in zip(d_pts, d_pts0):
+            a.copy_(b)
+        for a, b in zip(h_pts, h_pts0):
+            a.copy_(b)
+        flush.fill_(1.0)  # evict L2 (126 MB) between timed steps
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        total = 0.0
+        for _ in range(steps):
+            reset()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            barrier()
+            total += e0.elapsed_time(e1)
+        t = torch.tensor([total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    resident = lambda: step(d_X, d_y, d_pts)  # noqa: E731
+
+    def host_step():
+        step(h_X, h_y, h_pts)
+        if world > 1:  # the exchange of the evolved sets, from the host copies
+            for e in range(3):
+                d_pts[e].copy_(h_pts[e], non_blocking=True)
+                dist.all_gather_into_tensor(d_gather[e], d_pts[e])
+
+    for _ in range(max(args.warmup, 3)):
+        reset()
+        resident()
+    torch.cuda.synchronize()
+    dmma_peak, dfma_peak = ctx.fp64_peak()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.profile_enable(True)
+    for slot in range(3):
+        ctx.profile_read(slot)
+    launches0 = ctx.launches
+    total_ms = timed(resident, args.steps)
+    launches = ctx.launches - launches0
+    prof = [ctx.profile_read(slot) for slot in range(3)]
+    ctx.profile_enable(False)
+    clocks = sampler.stop()
+
+    reset()
+    host_step()  # warm the host path
+    e2e_ms = timed(host_step, args.steps)
+
+    ms_per_step = total_ms / args.steps
+    value = 1000.0 / ms_per_step
+    e2e_value = 1000.0 / (e2e_ms / args.steps)
+    h2d = sum(t.numel() * 8 for t in h_X + h_y + h_pts)
+    d2h = sum(t.numel() * 8 for t in h_pts) + 3 * 160
+
+    var_ms, var_n, var_flops = prof[0]
+    kb_ms, kb_n, kb_bytes = prof[1]
+    fa_ms, fa_n, fa_flops = prof[2]
+    achieved = var_flops / (var_ms * 1e-3) / 1e12 if var_ms > 0 else 0.0
+    # algorithmic flops of the reference formulation (2 Q N^2 per real query set, 16 Q N^2 complex)
+    alg_flops_step = 8 * nloc * (2 + 2 + 16) * float(N_TRAIN) ** 2 + (1 + 1 + 24 + 1.0 / 3.0) * float(N_TRAIN) ** 3
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "parallelism": f"points sharded over {world} GPU(s); models rebuilt redundantly; NCCL all-gather of evolved points",
+                   "l2": "512 MiB buffer written between timed steps; per-step working set (K* chunk 310-620 MB) exceeds L2"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "var_gemm_kernel (Z = K* W^T, fused row sum of squares; FP64 DMMA)", "achieved": achieved,
+                     "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak if dmma_peak > 0 else None, "traffic": None,
+                     "peak_source": "measured live by gple_measure_fp64_peak (register-resident DMMA.8x8x4 loop); MEASURED_PEAKS.json has no FP64 entry",
+                     "launches": var_n, "avg_launch_ms": var_ms / max(var_n, 1), "share_of_step": var_ms / total_ms,
+                     "flops_counted": "executed (triangular) flops rows*n*(n+128); the reference formulation K* K^-1 k^T would be 2x"},
+        "extra": {"fp64_dfma_peak_tflops": dfma_peak,
+                  "kernel_build_gbs": kb_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else None, "kernel_build_share": kb_ms / total_ms,
+                  "cholesky_inverse_tflops": fa_flops / (fa_ms * 1e-3) / 1e12 if fa_ms > 0 else None, "factorise_share": fa_ms / total_ms,
+                  "reference_formulation_tflops_equiv": alg_flops_step / (ms_per_step * 1e-3) / 1e12,
+                  "check": last_scalars},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        step_s, desc, cores = cpu_sample(sets)
+        line["cpu_baseline"] = {"value": 1.0 / step_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

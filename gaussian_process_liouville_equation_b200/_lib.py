@@ -58,6 +58,8 @@ SIGNATURES = {
     "gple_evolve": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, _dp, _sz, _dp, _sz, C.c_double, C.c_double]),
     "gple_new_point_predict": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),
     "gple_observables": (C.c_int, [_vp, C.c_int, _dp, _sz, C.c_double, C.c_int, _dp]),
+    "gple_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "gple_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
     "gple_measure_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
@@ -129,6 +131,15 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.gple_launch_count(self.h))
+
+    def profile_enable(self, on: bool):
+        self.check(self.lib.gple_profile_enable(self.h, int(on)))
+
+    def profile_read(self, slot: int):
+        """(total_ms, launches, work) of the profiled kernel since the last read."""
+        ms, n, w = C.c_double(), C.c_ulonglong(), C.c_double()
+        self.check(self.lib.gple_profile_read(self.h, int(slot), C.byref(ms), C.byref(n), C.byref(w)))
+        return ms.value, int(n.value), w.value
 
     def fp64_peak(self):
         a, b = C.c_double(), C.c_double()

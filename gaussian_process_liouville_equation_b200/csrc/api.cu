@@ -579,6 +579,54 @@ extern "C"
 		);
 	}
 
+	int gple_profile_enable(gple_ctx* ctx, int on)
+	{
+		if (ctx == nullptr)
+		{
+			return GPLE_ERR_ARG;
+		}
+		ctx->prof_on = on != 0;
+		return GPLE_OK;
+	}
+
+	int gple_profile_read(gple_ctx* ctx, int slot, double* total_ms, unsigned long long* launches, double* work)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(slot >= 0 && slot < 3, "gple_profile_read: unknown slot");
+				sync(ctx);
+				auto& p = ctx->prof[slot];
+				double tot = 0.0;
+				for (auto& e : p.ev)
+				{
+					float ms = 0.f;
+					GPLE_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
+					tot += ms;
+					cudaEventDestroy(e.first);
+					cudaEventDestroy(e.second);
+				}
+				p.ev.clear();
+				if (total_ms != nullptr)
+				{
+					*total_ms = tot;
+				}
+				if (launches != nullptr)
+				{
+					*launches = p.launches;
+				}
+				if (work != nullptr)
+				{
+					*work = p.work;
+				}
+				p.launches = 0;
+				p.work = 0.0;
+				return GPLE_OK;
+			}
+		);
+	}
+
 	int gple_measure_fp64_peak(gple_ctx* ctx, double* dmma_tflops, double* dfma_tflops)
 	{
 		return guarded(

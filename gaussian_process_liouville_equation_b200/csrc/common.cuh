@@ -94,6 +94,14 @@ struct gple_ctx
 	double* h_pinned = nullptr; // small pinned staging area for scalar read-backs
 	size_t h_pinned_count = 0;
 	int num_sms = 148;
+	// optional per-kernel event timing (gple_profile_*)
+	bool prof_on = false;
+	struct ProfSlot
+	{
+		std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+		double work = 0.0;
+		unsigned long long launches = 0;
+	} prof[3];
 };
 
 namespace gple
@@ -161,6 +169,35 @@ struct DeviceArray
 		(ctx)->launches++;                                                      \
 		GPLE_CUDA(cudaGetLastError());                                          \
 	} while (0)
+
+/// RAII event bracket around one or more launches of a profiled kernel
+struct ProfScope
+{
+	gple_ctx* ctx;
+	int slot;
+	cudaEvent_t e1 = nullptr;
+	ProfScope(gple_ctx* c, int s, double work, unsigned long long launches): ctx(c), slot(s)
+	{
+		if (!ctx->prof_on)
+		{
+			return;
+		}
+		cudaEvent_t e0;
+		GPLE_CUDA(cudaEventCreate(&e0));
+		GPLE_CUDA(cudaEventCreate(&e1));
+		GPLE_CUDA(cudaEventRecord(e0, ctx->stream));
+		ctx->prof[slot].ev.emplace_back(e0, e1);
+		ctx->prof[slot].work += work;
+		ctx->prof[slot].launches += launches;
+	}
+	~ProfScope()
+	{
+		if (e1 != nullptr)
+		{
+			cudaEventRecord(e1, ctx->stream);
+		}
+	}
+};
 
 // ---- parameter blocks passed by value to kernels -------------------------------------------------
 

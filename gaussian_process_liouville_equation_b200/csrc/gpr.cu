@@ -721,7 +721,15 @@ int train_common(gple_ctx* ctx, gple_model* m, const BlockSpec& spec, const Devi
 	int* d_info = ctx->ws.get<int>("train.info", 4);
 	const int tiles = n / 128;
 	GPLE_LAUNCH(ctx, build_cov_lower_kernel, dim3(tiles, tiles), 256, 0, spec, reinterpret_cast<const double2*>(m->X), N, Np, n, K);
-	potrf_trtri(ctx, K, m->W, n, d_info);
+	{
+		const unsigned long long before = ctx->launches;
+		ProfScope prof(ctx, GPLE_PROF_FACTORISE, 2.0 * double(n) * n * n / 3.0, 0);
+		potrf_trtri(ctx, K, m->W, n, d_info);
+		if (ctx->prof_on)
+		{
+			ctx->prof[GPLE_PROF_FACTORISE].launches += ctx->launches - before;
+		}
+	}
 	GPLE_LAUNCH(ctx, label_kernel, 1, 1024, 0, reinterpret_cast<const double2*>(y.dev), N, Np, m->is_complex, m->label, d_scal);
 	double* z = ctx->ws.get<double>("train.z", size_t(n));
 	GPLE_LAUNCH(ctx, trmv_lower_kernel, (n + 7) / 8, 256, 0, m->W, n, m->label, z);
@@ -958,9 +966,13 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 	{
 		const int rows_real = int(std::min<long long>(CHUNK_ROWS, total_rows - row0));
 		const int rows = int(round_up(size_t(rows_real), 128));
+		{
+			ProfScope prof(ctx, GPLE_PROF_KERNEL_BUILD, 8.0 * double(rows) * n, 1);
 		GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, reinterpret_cast<const double2*>(d_Xq), (long long)Q, row0, rows, reinterpret_cast<const double2*>(m->X), int(m->N), m->Np, n, m->v, A, pred);
+		}
 		if (d_var != nullptr || d_cut != nullptr)
 		{
+			ProfScope prof(ctx, GPLE_PROF_VARIANCE_GEMM, double(rows) * n * (double(n) + 128.0), 1);
 			GPLE_LAUNCH(ctx, var_gemm_kernel, rows / 128, gemm::THREADS, gemm::SMEM_BYTES, A, m->W, n, q);
 		}
 		else

@@ -156,6 +156,17 @@ extern "C"
 	int gple_observables(gple_ctx* ctx, int pes_model, const double* pts, size_t n, double mass, int pes_index, double out[9]);
 
 	/* ---- measurement helpers (bench.py) --------------------------------------------------------------- */
+	/* Per-kernel CUDA-event timing on the launching stream.  While enabled, every launch of the kernels below is
+	 * bracketed by an event pair; gple_profile_read synchronises, sums the elapsed times since the last read and
+	 * resets.  `work` is the executed work of those launches: FP64 flops (DMMA kernels) or HBM bytes (kernel build). */
+	enum gple_profile_slot
+	{
+		GPLE_PROF_VARIANCE_GEMM = 0, /* var_gemm_kernel: Z = K* W^T with fused row sum of squares; flops */
+		GPLE_PROF_KERNEL_BUILD = 1,	 /* kstar_kernel: K* rows + fused mean; bytes written */
+		GPLE_PROF_FACTORISE = 2		 /* potrf + trtri (all their launches together); flops = 2 n^3 / 3 */
+	};
+	int gple_profile_enable(gple_ctx* ctx, int on);
+	int gple_profile_read(gple_ctx* ctx, int slot, double* total_ms, unsigned long long* launches, double* work);
 	/* Register-resident DMMA / DFMA loops: measured FP64 tensor and vector peaks of this GPU, in TFLOP/s. */
 	int gple_measure_fp64_peak(gple_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
 
