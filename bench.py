@@ -30,6 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+from gaussian_process_liouville_equation_b200 import sharding  # noqa: E402
 from gaussian_process_liouville_equation_b200 import synthetic as syn  # noqa: E402
 
 N_TRAIN = 2048
@@ -164,14 +165,14 @@ def run_ours(args):
 
     sets, pts_all = make_inputs()
     # block partition of the evolved points (strong scaling); every rank keeps the full training sets
-    lo, hi = Q_POINTS * rank // world, Q_POINTS * (rank + 1) // world
+    lo, hi = sharding.partition(Q_POINTS, rank, world)
     nloc = hi - lo
     thetas = [THETA_R, THETA_C, THETA_R]
     d_X = [torch.from_numpy(s[0]).to(dev) for s in sets]
     d_y = [torch.from_numpy(np.ascontiguousarray(s[1]).view(np.float64)).to(dev) for s in sets]
     d_pts0 = [torch.from_numpy(p[lo:hi].copy()).to(dev) for p in pts_all]
     d_pts = [t.clone() for t in d_pts0]
-    d_gather = [torch.empty((Q_POINTS, 4), dtype=torch.float64, device=dev) for _ in range(3)] if world > 1 else None
+    gathered = [None, None, None]
     h_X = [torch.from_numpy(s[0]).pin_memory() for s in sets]
     h_y = [torch.from_numpy(np.ascontiguousarray(s[1]).view(np.float64)).pin_memory() for s in sets]
     h_pts0 = [torch.from_numpy(p[lo:hi].copy()).pin_memory() for p in pts_all]
@@ -203,7 +204,7 @@ def run_ours(args):
             lib.gple_model_destroy(ctx.h, h)
         if world > 1 and pts[0].is_cuda:
             for e in range(3):
-                dist.all_gather_into_tensor(d_gather[e], pts[e])
+                gathered[e] = sharding.all_gather_points(pts[e], Q_POINTS)
 
     def reset():
         for a, b in zip(d_pts, d_pts0):
@@ -242,7 +243,7 @@ def run_ours(args):
         if world > 1:  # the exchange of the evolved sets, from the host copies
             for e in range(3):
                 d_pts[e].copy_(h_pts[e], non_blocking=True)
-                dist.all_gather_into_tensor(d_gather[e], d_pts[e])
+                gathered[e] = sharding.all_gather_points(d_pts[e], Q_POINTS)
 
     for _ in range(max(args.warmup, 3)):
         reset()
@@ -288,7 +289,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "var_gemm_kernel (Z = K* W^T, fused row sum of squares; FP64 DMMA)", "achieved": achieved,
-                     "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak if dmma_peak > 0 else None, "traffic": None,
+                     "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak if dmma_peak > 0 else None, "traffic": 2.338e9 * (var_flops / max(var_n, 1)) / 8.442e10,
+                     "traffic_note": "ncu dram__bytes_read+write of a real-element launch (2.338 GB for 8.44e10 flops, profiles/r01_var_gemm_ncu_full.md), scaled by flops per launch",
                      "peak_source": "measured live by gple_measure_fp64_peak (register-resident DMMA.8x8x4 loop); MEASURED_PEAKS.json has no FP64 entry",
                      "launches": var_n, "avg_launch_ms": var_ms / max(var_n, 1), "share_of_step": var_ms / total_ms,
                      "flops_counted": "executed (triangular) flops rows*n*(n+128); the reference formulation K* K^-1 k^T would be 2x"},

@@ -1,0 +1,336 @@
+// gple_host.hpp -- C++ host mirror of the reference's hot-path headers over the C-ABI (include/gple_b200.h).
+//
+// Same class names, constructor arguments and getter semantics as the reference
+// (kaigu1997/gaussian_process_liouville_equation, gaussian_process_liouville_equation/ = gple/):
+//   gple/kernel.h          TrainingKernel (:111-280), PredictiveKernel (:336-403)
+//   gple/complex_kernel.h  TrainingComplexKernel (:150-318), PredictiveComplexKernel (:323-391)
+//   gple/predict.h         TrainingKernels (:89-143), calculate_* observables (:19-72)
+//   gple/evolve.h          evolve (:16-21)      gple/pes.h  adiabatic_potential / force / coupling (:47-59)
+//   gple/storage.h         PhaseSpacePoint (:232-297), ElementPoints / AllPoints (:327-329)
+// Eigen is not available, so containers are plain std types with the reference's memory layout
+// (PhasePoints = 2 x n column-major doubles; matrices column-major).  Objects are thin handles: the data lives
+// on the GPU, scalars are copied back eagerly, matrices lazily.  Header-only; link with libgple_b200.so.
+#pragma once
+#include "../../include/gple_b200.h"
+
+#include <array>
+#include <cassert>
+#include <complex>
+#include <limits>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+namespace gple_host
+{
+constexpr std::size_t NumPES = 2, PhaseDim = 2, NumElements = 3; // gple/stdafx.h:111-121 (lower-triangular elements)
+
+/// gple/stdafx.h:153 -- 2 x n, column-major: (x_0, p_0, x_1, p_1, ...)
+struct PhasePoints
+{
+	std::vector<double> d;
+	PhasePoints() = default;
+	explicit PhasePoints(std::size_t n): d(2 * n, 0.0) {}
+	std::size_t cols() const { return d.size() / 2; }
+	double& operator()(std::size_t row, std::size_t col) { return d[2 * col + row]; }
+	double operator()(std::size_t row, std::size_t col) const { return d[2 * col + row]; }
+	const double* data() const { return d.data(); }
+};
+using ParameterVector = std::vector<double>;												 // gple/kernel.h:10
+using ElementTrainingSet = std::tuple<PhasePoints, std::vector<std::complex<double>>>;		 // gple/kernel.h:14
+using ClassicalPhaseVector = std::array<double, PhaseDim>;									 // gple/stdafx.h:147
+
+/// gple/storage.h:232-297 (32 bytes, same layout)
+struct PhaseSpacePoint
+{
+	ClassicalPhaseVector r;
+	std::complex<double> rho;
+};
+static_assert(sizeof(PhaseSpacePoint) == 32, "PhaseSpacePoint must stay the reference's 32-byte AoS");
+using ElementPoints = std::vector<PhaseSpacePoint>;			 // gple/storage.h:327
+using AllPoints = std::array<ElementPoints, NumElements>;	 // lower-triangular order rho00, rho10, rho11
+
+class Context
+{
+public:
+	static gple_ctx* get(int device = 0)
+	{
+		static Context c(device);
+		return c.ctx;
+	}
+	static void check(int rc, const char* where, bool allow_not_spd = false)
+	{
+		if (rc == GPLE_OK || (allow_not_spd && rc == GPLE_ERR_NOT_SPD))
+		{
+			return;
+		}
+		throw std::runtime_error(std::string(where) + ": gple status " + std::to_string(rc) + ": " + gple_last_error(get()));
+	}
+
+private:
+	gple_ctx* ctx = nullptr;
+	explicit Context(int device)
+	{
+		if (gple_ctx_create(device, &ctx) != GPLE_OK)
+		{
+			throw std::runtime_error("gple_ctx_create failed: no CUDA device (there is no CPU fallback)");
+		}
+	}
+	~Context() { gple_ctx_destroy(ctx); }
+};
+
+struct ModelDeleter
+{
+	void operator()(gple_model* m) const { gple_model_destroy(Context::get(), m); }
+};
+using ModelHandle = std::unique_ptr<gple_model, ModelDeleter>;
+
+/// gple/opt.cpp:420-431
+inline void make_normal(double& d)
+{
+	if (!(d == d) || d == std::numeric_limits<double>::infinity() || d == -std::numeric_limits<double>::infinity())
+	{
+		d = std::numeric_limits<double>::max();
+	}
+}
+
+/// gple/kernel.h:111-280
+class TrainingKernel
+{
+public:
+	static constexpr std::size_t NumTotalParameters = 4;
+	template <typename T>
+	using ParameterArray = std::array<T, NumTotalParameters>;
+
+	TrainingKernel(const ParameterVector& Parameter, const ElementTrainingSet& TrainingSet, bool IsToCalculateError, bool IsToCalculateAverage, bool IsToCalculateDerivative):
+		Params(Parameter), Feature(std::get<0>(TrainingSet)), N(std::get<0>(TrainingSet).cols()),
+		Flags((IsToCalculateError ? GPLE_CALC_ERROR : 0u) | (IsToCalculateAverage ? GPLE_CALC_AVERAGE : 0u) | (IsToCalculateDerivative ? GPLE_CALC_DERIVATIVE : 0u))
+	{
+		assert(Parameter.size() == NumTotalParameters);
+		gple_model* m = nullptr;
+		Status = gple_train_real(Context::get(), Feature.data(), reinterpret_cast<const double*>(std::get<1>(TrainingSet).data()), N, Params.data(), Flags, &m, &S);
+		Context::check(Status, "TrainingKernel", true);
+		Handle.reset(m);
+	}
+	const ParameterVector& get_parameters() const { return Params; }
+	const PhasePoints& get_left_feature() const { return Feature; }
+	double get_rescale_factor() const { return S.rescale; }
+	double get_magnitude() const { return S.magnitude; }
+	double get_error() const { assert(Flags & GPLE_CALC_ERROR); return S.error; }
+	double get_population() const { assert(Flags & GPLE_CALC_AVERAGE); return S.population; }
+	ClassicalPhaseVector get_1st_order_average() const { assert(Flags & GPLE_CALC_AVERAGE); return {S.first_order[0], S.first_order[1]}; }
+	double get_purity() const { assert(Flags & GPLE_CALC_AVERAGE); return S.purity; }
+	ParameterArray<double> get_error_derivative() const { return arr(S.d_error); }
+	ParameterArray<double> get_population_derivative() const { return arr(S.d_population); }
+	ParameterArray<double> get_purity_derivative() const { return arr(S.d_purity); }
+	/// column-major N x N
+	std::vector<double> get_inverse() const { return field(GPLE_FIELD_INVERSE, N * N); }
+	std::vector<double> get_inverse_times_label() const { return field(GPLE_FIELD_INV_LABEL, N); }
+	const gple_model* handle() const { return Handle.get(); }
+	int status() const { return Status; }
+	std::size_t size() const { return N; }
+
+private:
+	ParameterVector Params;
+	PhasePoints Feature;
+	std::size_t N;
+	unsigned Flags;
+	int Status = GPLE_OK;
+	gple_real_scalars S{};
+	ModelHandle Handle;
+	static ParameterArray<double> arr(const double* p) { return {p[0], p[1], p[2], p[3]}; }
+	std::vector<double> field(int which, std::size_t count) const
+	{
+		std::vector<double> out(count);
+		Context::check(gple_model_get(Context::get(), Handle.get(), which, out.data()), "gple_model_get");
+		return out;
+	}
+};
+
+/// gple/kernel.h:336-403
+class PredictiveKernel
+{
+public:
+	PredictiveKernel(const PhasePoints& TestFeature, const TrainingKernel& kernel, bool IsToCalculateDerivative, const std::optional<std::vector<double>>& TestLabel = std::nullopt):
+		Variance(TestFeature.cols()), Cutoff(TestFeature.cols()), Prediction(TestFeature.cols())
+	{
+		const bool grad = IsToCalculateDerivative && TestLabel.has_value();
+		Context::check(
+			gple_predict_real(Context::get(), kernel.handle(), TestFeature.data(), TestFeature.cols(), TestLabel ? TestLabel->data() : nullptr, Prediction.data(), Variance.data(), Cutoff.data(), TestLabel ? &Error : nullptr, grad ? ErrorDerivatives.data() : nullptr),
+			"PredictiveKernel"
+		);
+	}
+	const std::vector<double>& get_variance() const { return Variance; }
+	const std::vector<double>& get_cutoff_prediction() const { return Cutoff; }
+	const std::vector<double>& get_prediction() const { return Prediction; }
+	double get_error() const { return Error; }
+	const std::array<double, 4>& get_error_derivative() const { return ErrorDerivatives; }
+
+private:
+	std::vector<double> Variance, Cutoff, Prediction;
+	double Error = std::numeric_limits<double>::quiet_NaN();
+	std::array<double, 4> ErrorDerivatives{};
+};
+
+/// gple/complex_kernel.h:150-318
+class TrainingComplexKernel
+{
+public:
+	static constexpr std::size_t NumTotalParameters = 8;
+	TrainingComplexKernel(const ParameterVector& Parameter, const ElementTrainingSet& TrainingSet, bool IsToCalculateError, bool IsToCalculateAverage, bool IsToCalculateDerivative):
+		Params(Parameter), N(std::get<0>(TrainingSet).cols()),
+		Flags((IsToCalculateError ? GPLE_CALC_ERROR : 0u) | (IsToCalculateAverage ? GPLE_CALC_AVERAGE : 0u) | (IsToCalculateDerivative ? GPLE_CALC_DERIVATIVE : 0u))
+	{
+		assert(Parameter.size() == NumTotalParameters);
+		gple_model* m = nullptr;
+		Status = gple_train_complex(Context::get(), std::get<0>(TrainingSet).data(), reinterpret_cast<const double*>(std::get<1>(TrainingSet).data()), N, Params.data(), Flags, &m, &S);
+		Context::check(Status, "TrainingComplexKernel", true);
+		Handle.reset(m);
+	}
+	const ParameterVector& get_parameters() const { return Params; }
+	double get_rescale_factor() const { return S.rescale; }
+	double get_magnitude() const { return S.magnitude; }
+	double get_error() const { assert(Flags & GPLE_CALC_ERROR); return S.error; }
+	double get_purity() const { assert(Flags & GPLE_CALC_AVERAGE); return S.purity; }
+	std::vector<std::complex<double>> get_upper_left_block_of_augmented_inverse() const { return cfield(GPLE_FIELD_UPPER_LEFT, N * N); }
+	std::vector<std::complex<double>> get_lower_left_block_of_augmented_inverse() const { return cfield(GPLE_FIELD_LOWER_LEFT, N * N); }
+	std::vector<std::complex<double>> get_upper_part_of_augmented_inverse_times_label() const { return cfield(GPLE_FIELD_INV_LABEL, N); }
+	const gple_model* handle() const { return Handle.get(); }
+	int status() const { return Status; }
+
+private:
+	ParameterVector Params;
+	std::size_t N;
+	unsigned Flags;
+	int Status = GPLE_OK;
+	gple_complex_scalars S{};
+	ModelHandle Handle;
+	std::vector<std::complex<double>> cfield(int which, std::size_t count) const
+	{
+		std::vector<std::complex<double>> out(count);
+		Context::check(gple_model_get(Context::get(), Handle.get(), which, reinterpret_cast<double*>(out.data())), "gple_model_get");
+		return out;
+	}
+};
+
+/// gple/complex_kernel.h:323-391
+class PredictiveComplexKernel
+{
+public:
+	PredictiveComplexKernel(const PhasePoints& TestFeature, const TrainingComplexKernel& kernel, bool /*IsToCalculateDerivative*/, const std::optional<std::vector<std::complex<double>>>& TestLabel = std::nullopt):
+		Variance(TestFeature.cols()), Cutoff(TestFeature.cols()), Prediction(TestFeature.cols())
+	{
+		Context::check(
+			gple_predict_complex(Context::get(), kernel.handle(), TestFeature.data(), TestFeature.cols(), TestLabel ? reinterpret_cast<const double*>(TestLabel->data()) : nullptr, reinterpret_cast<double*>(Prediction.data()), Variance.data(), reinterpret_cast<double*>(Cutoff.data()), TestLabel ? &Error : nullptr, nullptr),
+			"PredictiveComplexKernel"
+		);
+	}
+	const std::vector<double>& get_variance() const { return Variance; }
+	const std::vector<std::complex<double>>& get_cutoff_prediction() const { return Cutoff; }
+	double get_error() const { return Error; }
+
+private:
+	std::vector<double> Variance;
+	std::vector<std::complex<double>> Cutoff, Prediction;
+	double Error = std::numeric_limits<double>::quiet_NaN();
+};
+
+/// gple/predict.h:89-143 -- the (up to) three element models of one time step
+class TrainingKernels
+{
+public:
+	/// gple/predict.cpp:390-393 (error = true, average = true, derivative = false); empty elements stay nullopt
+	TrainingKernels(const std::array<ParameterVector, NumElements>& ParameterVectors, const AllPoints& density)
+	{
+		for (std::size_t e = 0; e < NumElements; e++)
+		{
+			if (density[e].empty())
+			{
+				continue;
+			}
+			ElementTrainingSet ts{PhasePoints(density[e].size()), std::vector<std::complex<double>>(density[e].size())};
+			for (std::size_t i = 0; i < density[e].size(); i++) // gple/predict.cpp:246-280
+			{
+				std::get<0>(ts)(0, i) = density[e][i].r[0];
+				std::get<0>(ts)(1, i) = density[e][i].r[1];
+				std::get<1>(ts)[i] = density[e][i].rho;
+			}
+			if (e == 1)
+			{
+				OffDiagonal.emplace(ParameterVectors[e], ts, true, true, false);
+			}
+			else
+			{
+				Diagonal[e / 2].emplace(ParameterVectors[e], ts, true, true, false);
+			}
+		}
+	}
+	double calculate_population() const // gple/predict.cpp:395-406
+	{
+		double r = 0.0;
+		for (const auto& k : Diagonal)
+		{
+			r += k ? k->get_population() : 0.0;
+		}
+		return r;
+	}
+	double calculate_purity() const // gple/predict.cpp:439-463
+	{
+		double r = OffDiagonal ? 2.0 * OffDiagonal->get_purity() : 0.0;
+		for (const auto& k : Diagonal)
+		{
+			r += k ? k->get_purity() : 0.0;
+		}
+		return r;
+	}
+	const gple_model* handle(std::size_t element) const
+	{
+		if (element == 1)
+		{
+			return OffDiagonal ? OffDiagonal->handle() : nullptr;
+		}
+		return Diagonal[element / 2] ? Diagonal[element / 2]->handle() : nullptr;
+	}
+	std::array<std::optional<TrainingKernel>, NumPES> Diagonal;
+	std::optional<TrainingComplexKernel> OffDiagonal;
+};
+
+/// gple/evolve.h:16-21 with the GPR-backed predict_distribution of gple/main.cpp:75-101
+inline void evolve(AllPoints& density, double mass, double dt, const TrainingKernels& kernels, int pes_model)
+{
+	Context::check(
+		gple_evolve(Context::get(), pes_model, kernels.handle(0), kernels.handle(1), kernels.handle(2), reinterpret_cast<double*>(density[0].data()), density[0].size(), reinterpret_cast<double*>(density[1].data()), density[1].size(), reinterpret_cast<double*>(density[2].data()), density[2].size(), mass, dt),
+		"evolve"
+	);
+}
+
+/// gple/pes.h:47 (one position)
+inline std::array<double, NumPES> adiabatic_potential(double x, int pes_model)
+{
+	double E[2], F[3], D[1];
+	Context::check(gple_pes(Context::get(), pes_model, &x, 1, E, F, D), "adiabatic_potential");
+	return {E[0], E[1]};
+}
+
+/// gple/predict.cpp:65-87
+inline std::array<double, NumPES> calculate_population_each_surface(const AllPoints& density, double mass, int pes_model)
+{
+	std::array<double, NumPES> r{0.0, 0.0};
+	for (std::size_t s = 0; s < NumPES; s++)
+	{
+		const ElementPoints& pts = density[2 * s];
+		if (!pts.empty())
+		{
+			double o[9];
+			Context::check(gple_observables(Context::get(), pes_model, reinterpret_cast<const double*>(pts.data()), pts.size(), mass, int(s), o), "observables");
+			r[s] = o[0];
+		}
+	}
+	const double sum = r[0] + r[1];
+	return {r[0] / sum, r[1] / sum};
+}
+
+} // namespace gple_host
