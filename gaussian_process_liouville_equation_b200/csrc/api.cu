@@ -169,6 +169,7 @@ extern "C"
 		cudaSetDevice(ctx->device);
 		cudaStreamSynchronize(ctx->stream);
 		ctx->ws.release();
+		ctx->pool.release();
 		if (ctx->h_pinned != nullptr)
 		{
 			cudaFreeHost(ctx->h_pinned);
@@ -283,12 +284,12 @@ extern "C"
 	}
 	int gple_model_destroy(gple_ctx* ctx, gple_model* m)
 	{
-		if (ctx != nullptr)
+		if (ctx == nullptr)
 		{
-			cudaSetDevice(ctx->device);
-			cudaStreamSynchronize(ctx->stream);
+			return GPLE_ERR_ARG;
 		}
-		free_model(m);
+		cudaSetDevice(ctx->device);
+		free_model(ctx, m); // buffers go back to the context's pool; reuse is ordered on the context's stream
 		return GPLE_OK;
 	}
 
@@ -468,7 +469,7 @@ extern "C"
 				}
 				if (rc != GPLE_OK)
 				{
-					free_model(m);
+					free_model(ctx, m);
 					*value = std::nan("");
 					return rc;
 				}
@@ -496,7 +497,7 @@ extern "C"
 						grad[p] = trn_grad[p] + vg[p];
 					}
 				}
-				free_model(m);
+				free_model(ctx, m);
 				return GPLE_OK;
 			}
 		);

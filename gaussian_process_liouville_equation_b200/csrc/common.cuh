@@ -81,6 +81,44 @@ struct Workspace
 		bufs.clear();
 	}
 };
+/// Size-bucketed free list for the per-model device buffers: a model created and destroyed every time step (or every
+/// optimiser evaluation) must not pay cudaMalloc / cudaFree (device-wide syncs, and peer mapping once NCCL is up).
+struct BlockPool
+{
+	std::multimap<size_t, void*> free_blocks;
+	std::map<void*, size_t> sizes;
+	void* alloc(size_t bytes)
+	{
+		bytes = round_up(bytes == 0 ? 1 : bytes, 512);
+		auto it = free_blocks.lower_bound(bytes);
+		if (it != free_blocks.end() && it->first <= bytes + bytes / 4)
+		{
+			void* p = it->second;
+			free_blocks.erase(it);
+			return p;
+		}
+		void* p = nullptr;
+		GPLE_CUDA(cudaMalloc(&p, bytes));
+		sizes[p] = bytes;
+		return p;
+	}
+	void free(void* p)
+	{
+		if (p != nullptr)
+		{
+			free_blocks.emplace(sizes.at(p), p);
+		}
+	}
+	void release()
+	{
+		for (auto& kv : sizes)
+		{
+			cudaFree(kv.first);
+		}
+		sizes.clear();
+		free_blocks.clear();
+	}
+};
 } // namespace gple
 
 struct gple_ctx
@@ -91,6 +129,7 @@ struct gple_ctx
 	unsigned long long launches = 0;
 	std::string last_error;
 	gple::Workspace ws;
+	gple::BlockPool pool; // device buffers of the element models
 	double* h_pinned = nullptr; // small pinned staging area for scalar read-backs
 	size_t h_pinned_count = 0;
 	int num_sms = 148;

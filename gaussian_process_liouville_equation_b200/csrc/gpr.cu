@@ -710,13 +710,13 @@ constexpr int SCAL_COUNT = 16;
 int train_common(gple_ctx* ctx, gple_model* m, const BlockSpec& spec, const DeviceArray<double>& X, const DeviceArray<double>& y, double* d_scal)
 {
 	const int N = int(m->N), Np = m->Np, n = m->n;
-	GPLE_CUDA(cudaMalloc(&m->X, size_t(2) * Np * sizeof(double)));
+	m->X = static_cast<double*>(ctx->pool.alloc(size_t(2) * Np * sizeof(double)));
 	GPLE_CUDA(cudaMemsetAsync(m->X, 0, size_t(2) * Np * sizeof(double), ctx->stream));
 	GPLE_CUDA(cudaMemcpyAsync(m->X, X.dev, size_t(2) * N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-	GPLE_CUDA(cudaMalloc(&m->W, size_t(n) * n * sizeof(double)));
-	GPLE_CUDA(cudaMalloc(&m->v, size_t(n) * sizeof(double)));
-	GPLE_CUDA(cudaMalloc(&m->label, size_t(n) * sizeof(double)));
-	GPLE_CUDA(cudaMalloc(&m->kinv_diag, size_t(3) * n * sizeof(double)));
+	m->W = static_cast<double*>(ctx->pool.alloc(size_t(n) * n * sizeof(double)));
+	m->v = static_cast<double*>(ctx->pool.alloc(size_t(n) * sizeof(double)));
+	m->label = static_cast<double*>(ctx->pool.alloc(size_t(n) * sizeof(double)));
+	m->kinv_diag = static_cast<double*>(ctx->pool.alloc(size_t(3) * n * sizeof(double)));
 	double* K = ctx->ws.get<double>("train.K", size_t(n) * n);
 	int* d_info = ctx->ws.get<int>("train.info", 4);
 	const int tiles = n / 128;
@@ -772,7 +772,7 @@ void gpr_setup_attributes()
 	done = true;
 }
 
-void free_model(gple_model* m)
+void free_model(gple_ctx* ctx, gple_model* m)
 {
 	if (m == nullptr)
 	{
@@ -780,10 +780,7 @@ void free_model(gple_model* m)
 	}
 	for (double* p : {m->X, m->W, m->v, m->label, m->kinv_diag, m->Kinv, m->dv})
 	{
-		if (p != nullptr)
-		{
-			cudaFree(p);
-		}
+		ctx->pool.free(p); // stream-ordered reuse: every consumer runs on ctx->stream
 	}
 	delete m;
 }
@@ -795,7 +792,7 @@ void ensure_full_inverse(gple_ctx* ctx, gple_model* m)
 		return;
 	}
 	const int n = m->n;
-	GPLE_CUDA(cudaMalloc(&m->Kinv, size_t(n) * n * sizeof(double)));
+	m->Kinv = static_cast<double*>(ctx->pool.alloc(size_t(n) * n * sizeof(double)));
 	double* U = ctx->ws.get<double>("inv.U", size_t(n) * n);
 	GPLE_LAUNCH(ctx, transpose_kernel, dim3(n / 32, n / 32), dim3(32, 8), 0, m->W, U, n);
 	gemm::GemmArgs g{};
@@ -869,7 +866,7 @@ int train_real(gple_ctx* ctx, const double* X_, const double* y_, size_t N, cons
 	}
 	catch (...)
 	{
-		free_model(m);
+		free_model(ctx, m);
 		throw;
 	}
 	*out_model = m;
@@ -939,7 +936,7 @@ int train_complex(gple_ctx* ctx, const double* X_, const double* y_, size_t N, c
 	}
 	catch (...)
 	{
-		free_model(m);
+		free_model(ctx, m);
 		throw;
 	}
 	*out_model = m;

@@ -283,7 +283,7 @@ void real_derivatives(gple_ctx* ctx, gple_model* m, unsigned flags, const double
 	ensure_full_inverse(ctx, m);
 	if (m->dv == nullptr)
 	{
-		GPLE_CUDA(cudaMalloc(&m->dv, size_t(4) * n * sizeof(double)));
+		m->dv = static_cast<double*>(ctx->pool.alloc(size_t(4) * n * sizeof(double)));
 	}
 	double* dd = ctx->ws.get<double>("deriv.dd", size_t(4) * n);
 	double* tmp = ctx->ws.get<double>("deriv.tmp", size_t(6) * n);

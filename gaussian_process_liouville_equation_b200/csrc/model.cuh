@@ -25,7 +25,7 @@ struct gple_model
 
 namespace gple
 {
-void free_model(gple_model* m);
+void free_model(gple_ctx* ctx, gple_model* m);
 /// Kinv = W^T W (full symmetric), cached in the model
 void ensure_full_inverse(gple_ctx* ctx, gple_model* m);
 } // namespace gple
