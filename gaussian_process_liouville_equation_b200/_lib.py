@@ -58,6 +58,8 @@ SIGNATURES = {
     "gple_evolve": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, _dp, _sz, _dp, _sz, C.c_double, C.c_double]),
     "gple_new_point_predict": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),
     "gple_observables": (C.c_int, [_vp, C.c_int, _dp, _sz, C.c_double, C.c_int, _dp]),
+    "gple_tune_variance_gemm": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "gple_set_variance_gemm_variant": (C.c_int, [C.c_int]),
     "gple_profile_enable": (C.c_int, [_vp, C.c_int]),
     "gple_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
     "gple_measure_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -140,6 +142,11 @@ class Context:
         ms, n, w = C.c_double(), C.c_ulonglong(), C.c_double()
         self.check(self.lib.gple_profile_read(self.h, int(slot), C.byref(ms), C.byref(n), C.byref(w)))
         return ms.value, int(n.value), w.value
+
+    def tune_variance_gemm(self, variant: int, rows: int, n: int, iters: int = 5) -> float:
+        ms = C.c_double()
+        self.check(self.lib.gple_tune_variance_gemm(self.h, variant, rows, n, iters, C.byref(ms)))
+        return ms.value
 
     def fp64_peak(self):
         a, b = C.c_double(), C.c_double()

@@ -580,6 +580,24 @@ extern "C"
 		);
 	}
 
+	int gple_tune_variance_gemm(gple_ctx* ctx, int variant, int rows, int n, int iters, double* ms_per_launch)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(rows > 0 && rows % 128 == 0 && n > 0 && n % 128 == 0 && iters > 0 && ms_per_launch != nullptr, "gple_tune_variance_gemm: rows and n must be multiples of 128");
+				*ms_per_launch = bench_variance_gemm(ctx, variant, rows, n, iters);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_set_variance_gemm_variant(int variant)
+	{
+		return set_variance_gemm_variant(variant) == 0 ? GPLE_OK : GPLE_ERR_ARG;
+	}
+
 	int gple_profile_enable(gple_ctx* ctx, int on)
 	{
 		if (ctx == nullptr)

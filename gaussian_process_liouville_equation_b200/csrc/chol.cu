@@ -163,11 +163,11 @@ void run_gemm(gple_ctx* ctx, bool b_nn, const gemm::GemmArgs& a)
 	const dim3 grid(a.N / gemm::BN, a.M / gemm::BM);
 	if (b_nn)
 	{
-		GPLE_LAUNCH(ctx, gemm::gemm_kernel<true>, grid, gemm::THREADS, gemm::SMEM_BYTES, a);
+		GPLE_LAUNCH(ctx, (gemm::gemm_kernel<gemm::DefaultConfig, true>), grid, gemm::DefaultConfig::THREADS, gemm::DefaultConfig::SMEM_BYTES, a);
 	}
 	else
 	{
-		GPLE_LAUNCH(ctx, gemm::gemm_kernel<false>, grid, gemm::THREADS, gemm::SMEM_BYTES, a);
+		GPLE_LAUNCH(ctx, (gemm::gemm_kernel<gemm::DefaultConfig, false>), grid, gemm::DefaultConfig::THREADS, gemm::DefaultConfig::SMEM_BYTES, a);
 	}
 }
 
@@ -299,8 +299,8 @@ void chol_setup_attributes()
 	{
 		return;
 	}
-	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SMEM_BYTES)));
-	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SMEM_BYTES)));
+	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::DefaultConfig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::DefaultConfig::SMEM_BYTES)));
+	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::DefaultConfig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::DefaultConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LEAF_SMEM)));
 	done = true;
 }

@@ -2,10 +2,9 @@
 //
 // On B200 every f64 `mma.sync` shape lowers to the native DMMA.8x8x4 (checked with cuobjdump), and
 // tcgen05 has no f64 kind, so the FP64 tensor path is warp-level m8n8k4 with register accumulators.
-// CTA tile 128 x 128 x 16, 8 warps (2 x 4), warp tile 64 x 32 = 8 x 4 DMMA tiles (64 accumulator
-// doubles per thread), operands staged in shared memory by a 4-stage cp.async (LDGSTS) pipeline.
-// Shared-memory pitches are chosen so that every fragment load (8 rows x 4 k, one double per lane) hits
-// 16 distinct 8-byte banks per half-warp: pitch = 4 (mod 16) doubles.
+// CTA tile 128 x 128 x BK, WARPS_M x WARPS_N warps, operands staged in shared memory by a multi-stage
+// cp.async (LDGSTS) pipeline.  Shared-memory pitches are chosen so that every fragment load (8 rows x 4 k,
+// one double per lane) hits 16 distinct 8-byte banks per half-warp: pitch = 4 (mod 16) doubles.
 //
 // All matrices are ROW-MAJOR with leading dimension `ld` and padded to multiples of 128 (symmetric
 // matrices make the reference's column-major layout identical).  Two operand forms:
@@ -20,14 +19,26 @@ namespace gple
 {
 namespace gemm
 {
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 256;
-constexpr int KP = BK + 4;	  // pitch of a K-contiguous tile [rows][KP]
-constexpr int NP = BN + 4;	  // pitch of an N-contiguous B tile [BK][NP]
-constexpr int A_STAGE = BM * KP; // doubles
-constexpr int B_STAGE_NT = BN * KP;
-constexpr int B_STAGE_NN = BK * NP;
-constexpr int B_STAGE = B_STAGE_NT > B_STAGE_NN ? B_STAGE_NT : B_STAGE_NN;
-constexpr size_t SMEM_BYTES = size_t(STAGES) * (A_STAGE + B_STAGE) * sizeof(double);
+constexpr int BM = 128, BN = 128;
+
+/// Tile configuration.  BK_ in {16, 32}; warp tile = (128 / WARPS_M_) x (128 / WARPS_N_).
+template <int BK_, int STAGES_, int WARPS_M_, int WARPS_N_>
+struct Config
+{
+	static constexpr int BK = BK_, STAGES = STAGES_, WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;
+	static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+	static constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N; // warp tile
+	static constexpr int MI = WTM / 8, NJ = WTN / 8;			 // DMMA tiles per warp
+	static constexpr int KP = BK + 4;							 // pitch of a K-contiguous tile [rows][KP]
+	static constexpr int NP = BN + 4;							 // pitch of an N-contiguous B tile [BK][NP]
+	static constexpr int A_STAGE = BM * KP;						 // doubles
+	static constexpr int B_STAGE_NT = BN * KP, B_STAGE_NN = BK * NP;
+	static constexpr int B_STAGE = B_STAGE_NT > B_STAGE_NN ? B_STAGE_NT : B_STAGE_NN;
+	static constexpr size_t SMEM_BYTES = size_t(STAGES) * (A_STAGE + B_STAGE) * sizeof(double);
+	static_assert(KP % 16 == 4 && NP % 16 == 4, "pitch must be 4 mod 16 doubles for conflict-free fragment loads");
+};
+/// general GEMMs (Cholesky / inverse / gradients)
+using DefaultConfig = Config<16, 4, 2, 4>;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
@@ -50,59 +61,62 @@ __device__ __forceinline__ void dmma884(double (&c)[2], const double a, const do
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-/// Copy a K-contiguous 128 x 16 tile (rows r0.., k from k0) of a row-major matrix into [128][KP].
+/// Copy a K-contiguous 128 x BK tile of a row-major matrix into [128][KP].
+template <typename C>
 __device__ __forceinline__ void load_tile_kmajor(double* s, const double* __restrict__ g, const size_t ld, const int tid)
 {
+	constexpr int CH = C::BK / 2; // 16-byte chunks per row
 #pragma unroll
-	for (int i = 0; i < (128 * BK / 2) / THREADS; i++)
+	for (int i = 0; i < (128 * CH) / C::THREADS; i++)
 	{
-		const int c = tid + i * THREADS;
-		const int row = c >> 3, ch = c & 7;
-		cp_async16(s + row * KP + ch * 2, g + size_t(row) * ld + ch * 2);
+		const int c = tid + i * C::THREADS;
+		const int row = c / CH, ch = c % CH;
+		cp_async16(s + row * C::KP + ch * 2, g + size_t(row) * ld + ch * 2);
 	}
 }
-/// Copy an N-contiguous 16 x 128 tile (k rows, n from n0) into [16][NP].
+/// Copy an N-contiguous BK x 128 tile (k rows) into [BK][NP].
+template <typename C>
 __device__ __forceinline__ void load_tile_nmajor(double* s, const double* __restrict__ g, const size_t ld, const int tid)
 {
 #pragma unroll
-	for (int i = 0; i < (BK * 128 / 2) / THREADS; i++)
+	for (int i = 0; i < (C::BK * 64) / C::THREADS; i++)
 	{
-		const int c = tid + i * THREADS;
+		const int c = tid + i * C::THREADS;
 		const int row = c >> 6, ch = c & 63;
-		cp_async16(s + row * NP + ch * 2, g + size_t(row) * ld + ch * 2);
+		cp_async16(s + row * C::NP + ch * 2, g + size_t(row) * ld + ch * 2);
 	}
 }
 
-/// One 16-deep stage of the warp tile: 4 k-steps x (8 + 4 fragment loads, 32 DMMA).
-template <bool B_NN>
-__device__ __forceinline__ void compute_stage(double (&acc)[8][4][2], const double* __restrict__ As, const double* __restrict__ Bs, const int wm, const int wn, const int g, const int t)
+/// One BK-deep stage of the warp tile: BK / 4 k-steps x (MI + NJ fragment loads, MI * NJ DMMA).
+template <typename C, bool B_NN>
+__device__ __forceinline__ void compute_stage(double (&acc)[C::MI][C::NJ][2], const double* __restrict__ As, const double* __restrict__ Bs, const int wm, const int wn, const int g, const int t)
 {
 #pragma unroll
-	for (int kk = 0; kk < BK / 4; kk++)
+	for (int kk = 0; kk < C::BK / 4; kk++)
 	{
-		double a[8], b[4];
+		double a[C::MI], b[C::NJ];
 #pragma unroll
-		for (int i = 0; i < 8; i++)
+		for (int i = 0; i < C::MI; i++)
 		{
-			a[i] = As[(wm * 64 + i * 8 + g) * KP + kk * 4 + t];
+			a[i] = As[(wm * C::WTM + i * 8 + g) * C::KP + kk * 4 + t];
 		}
 #pragma unroll
-		for (int j = 0; j < 4; j++)
+		for (int j = 0; j < C::NJ; j++)
 		{
 			if (B_NN)
 			{
-				b[j] = Bs[(kk * 4 + t) * NP + wn * 32 + j * 8 + g];
+				b[j] = Bs[(kk * 4 + t) * C::NP + wn * C::WTN + j * 8 + g];
 			}
 			else
 			{
-				b[j] = Bs[(wn * 32 + j * 8 + g) * KP + kk * 4 + t];
+				b[j] = Bs[(wn * C::WTN + j * 8 + g) * C::KP + kk * 4 + t];
 			}
 		}
 #pragma unroll
-		for (int i = 0; i < 8; i++)
+		for (int i = 0; i < C::MI; i++)
 		{
 #pragma unroll
-			for (int j = 0; j < 4; j++)
+			for (int j = 0; j < C::NJ; j++)
 			{
 				dmma884(acc[i][j], a[i], b[j]);
 			}
@@ -110,13 +124,14 @@ __device__ __forceinline__ void compute_stage(double (&acc)[8][4][2], const doub
 	}
 }
 
-__device__ __forceinline__ void zero_acc(double (&acc)[8][4][2])
+template <typename C>
+__device__ __forceinline__ void zero_acc(double (&acc)[C::MI][C::NJ][2])
 {
 #pragma unroll
-	for (int i = 0; i < 8; i++)
+	for (int i = 0; i < C::MI; i++)
 	{
 #pragma unroll
-		for (int j = 0; j < 4; j++)
+		for (int j = 0; j < C::NJ; j++)
 		{
 			acc[i][j][0] = 0.0;
 			acc[i][j][1] = 0.0;
@@ -128,10 +143,10 @@ __device__ __forceinline__ void zero_acc(double (&acc)[8][4][2])
 enum Tri : int
 {
 	FULL = 0,
-	A_LOWER = 1, // A[m][k] == 0 for k > m   (k_end = m0 + BM)
+	A_LOWER = 1,	// A[m][k] == 0 for k > m   (k_end = m0 + BM)
 	B_LOWER_NT = 2, // NT: B[n][k] == 0 for k > n   (k_end = n0 + BN)
 	B_LOWER_NN = 4, // NN: B[k][n] == 0 for n > k   (k_begin = n0)
-	A_UPPER = 8, // A[m][k] == 0 for k < m   (k_begin = m0)
+	A_UPPER = 8,	// A[m][k] == 0 for k < m   (k_begin = m0)
 	B_UPPER_NT = 16 // NT: B[n][k] == 0 for k < n  (k_begin = n0)
 };
 
@@ -141,26 +156,26 @@ struct GemmArgs
 	const double* B;
 	double* C;
 	size_t lda, ldb, ldc;
-	int M, N, K; // multiples of 128 / 128 / 16
+	int M, N, K; // multiples of 128
 	double alpha, beta;
 	int tri;		// bitmask of Tri
 	int lower_only; // skip output tiles strictly above the diagonal (SYRK-style)
 };
 
 /// C = beta * C + alpha * A * op(B)
-template <bool B_NN>
-__global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const GemmArgs p)
+template <typename C, bool B_NN>
+__global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const GemmArgs p)
 {
 	extern __shared__ __align__(16) double smem[];
 	double* As = smem;
-	double* Bs = smem + STAGES * A_STAGE;
+	double* Bs = smem + C::STAGES * C::A_STAGE;
 	const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
 	if (p.lower_only && n0 > m0)
 	{
 		return;
 	}
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
+	const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N, g = lane >> 2, t = lane & 3;
 	int kb = 0, ke = p.K;
 	if (p.tri & A_LOWER)
 	{
@@ -182,54 +197,54 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const GemmArgs p)
 	{
 		kb = max(kb, n0);
 	}
-	const int nk = ke > kb ? (ke - kb) / BK : 0;
+	const int nk = ke > kb ? (ke - kb) / C::BK : 0;
 	const double* Ag = p.A + size_t(m0) * p.lda + kb;
 	const double* Bg = B_NN ? p.B + size_t(kb) * p.ldb + n0 : p.B + size_t(n0) * p.ldb + kb;
 
-	double acc[8][4][2];
-	zero_acc(acc);
+	double acc[C::MI][C::NJ][2];
+	zero_acc<C>(acc);
 
 	auto issue = [&](const int kt)
 	{
 		if (kt < nk)
 		{
-			const int slot = kt % STAGES;
-			load_tile_kmajor(As + slot * A_STAGE, Ag + size_t(kt) * BK, p.lda, tid);
+			const int slot = kt % C::STAGES;
+			load_tile_kmajor<C>(As + slot * C::A_STAGE, Ag + size_t(kt) * C::BK, p.lda, tid);
 			if (B_NN)
 			{
-				load_tile_nmajor(Bs + slot * B_STAGE, Bg + size_t(kt) * BK * p.ldb, p.ldb, tid);
+				load_tile_nmajor<C>(Bs + slot * C::B_STAGE, Bg + size_t(kt) * C::BK * p.ldb, p.ldb, tid);
 			}
 			else
 			{
-				load_tile_kmajor(Bs + slot * B_STAGE, Bg + size_t(kt) * BK, p.ldb, tid);
+				load_tile_kmajor<C>(Bs + slot * C::B_STAGE, Bg + size_t(kt) * C::BK, p.ldb, tid);
 			}
 		}
 		cp_async_commit();
 	};
 #pragma unroll
-	for (int s = 0; s < STAGES - 1; s++)
+	for (int s = 0; s < C::STAGES - 1; s++)
 	{
 		issue(s);
 	}
 	for (int kt = 0; kt < nk; kt++)
 	{
-		cp_async_wait<STAGES - 2>();
+		cp_async_wait<C::STAGES - 2>();
 		__syncthreads();
-		issue(kt + STAGES - 1);
-		const int slot = kt % STAGES;
-		compute_stage<B_NN>(acc, As + slot * A_STAGE, Bs + slot * B_STAGE, wm, wn, g, t);
+		issue(kt + C::STAGES - 1);
+		const int slot = kt % C::STAGES;
+		compute_stage<C, B_NN>(acc, As + slot * C::A_STAGE, Bs + slot * C::B_STAGE, wm, wn, g, t);
 	}
 	cp_async_wait<0>();
 
 	// epilogue: each lane owns (row, 2t..2t+1) of every 8x8 tile -> 16-byte row-major stores
 #pragma unroll
-	for (int i = 0; i < 8; i++)
+	for (int i = 0; i < C::MI; i++)
 	{
-		const int row = m0 + wm * 64 + i * 8 + g;
+		const int row = m0 + wm * C::WTM + i * 8 + g;
 #pragma unroll
-		for (int j = 0; j < 4; j++)
+		for (int j = 0; j < C::NJ; j++)
 		{
-			const int col = n0 + wn * 32 + j * 8 + 2 * t;
+			const int col = n0 + wn * C::WTN + j * 8 + 2 * t;
 			double2* dst = reinterpret_cast<double2*>(p.C + size_t(row) * p.ldc + col);
 			double2 v = make_double2(p.alpha * acc[i][j][0], p.alpha * acc[i][j][1]);
 			if (p.beta != 0.0)

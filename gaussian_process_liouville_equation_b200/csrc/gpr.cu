@@ -153,15 +153,16 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 
 /// One CTA owns 128 query rows and walks all n-tiles; the cp.async pipeline runs across n-tile boundaries
 /// (flattened (n-tile, k-step) sequence) so the tensor pipe never drains.  The squared accumulators are
-/// folded into 8 per-thread row sums; no Z is ever written.
-__global__ void __launch_bounds__(gemm::THREADS, 1) var_gemm_kernel(const double* __restrict__ A, const double* __restrict__ W, const int n, double* __restrict__ q)
+/// folded into per-thread row sums; no Z is ever written.
+template <typename C>
+__global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* __restrict__ A, const double* __restrict__ W, const int n, double* __restrict__ q)
 {
 	using namespace gemm;
 	extern __shared__ __align__(16) double smem[];
 	double* As = smem;
-	double* Bs = smem + STAGES * A_STAGE;
+	double* Bs = smem + C::STAGES * C::A_STAGE;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
+	const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N, g = lane >> 2, t = lane & 3;
 	const int m0 = blockIdx.x * BM;
 	const int T = n / BN;
 	const double* Ag = A + size_t(m0) * n;
@@ -171,10 +172,10 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) var_gemm_kernel(const double
 	{
 		if (l_nt < T)
 		{
-			load_tile_kmajor(As + l_slot * A_STAGE, Ag + size_t(l_kt) * BK, size_t(n), tid);
-			load_tile_kmajor(Bs + l_slot * B_STAGE, W + size_t(l_nt) * BN * n + size_t(l_kt) * BK, size_t(n), tid);
-			l_slot = (l_slot + 1 == STAGES) ? 0 : l_slot + 1;
-			if (++l_kt == (l_nt + 1) * (BN / BK))
+			load_tile_kmajor<C>(As + l_slot * C::A_STAGE, Ag + size_t(l_kt) * C::BK, size_t(n), tid);
+			load_tile_kmajor<C>(Bs + l_slot * C::B_STAGE, W + size_t(l_nt) * BN * n + size_t(l_kt) * C::BK, size_t(n), tid);
+			l_slot = (l_slot + 1 == C::STAGES) ? 0 : l_slot + 1;
+			if (++l_kt == (l_nt + 1) * (BN / C::BK))
 			{
 				l_kt = 0;
 				l_nt++;
@@ -183,35 +184,35 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) var_gemm_kernel(const double
 		cp_async_commit();
 	};
 #pragma unroll
-	for (int s = 0; s < STAGES - 1; s++)
+	for (int s = 0; s < C::STAGES - 1; s++)
 	{
 		issue();
 	}
-	double rowsum[8];
+	double rowsum[C::MI];
 #pragma unroll
-	for (int i = 0; i < 8; i++)
+	for (int i = 0; i < C::MI; i++)
 	{
 		rowsum[i] = 0.0;
 	}
-	double acc[8][4][2];
+	double acc[C::MI][C::NJ][2];
 	int c_slot = 0;
 	for (int nt = 0; nt < T; nt++)
 	{
-		zero_acc(acc);
-		const int steps = (nt + 1) * (BN / BK);
+		zero_acc<C>(acc);
+		const int steps = (nt + 1) * (BN / C::BK);
 		for (int kt = 0; kt < steps; kt++)
 		{
-			cp_async_wait<STAGES - 2>();
+			cp_async_wait<C::STAGES - 2>();
 			__syncthreads();
 			issue();
-			compute_stage<false>(acc, As + c_slot * A_STAGE, Bs + c_slot * B_STAGE, wm, wn, g, t);
-			c_slot = (c_slot + 1 == STAGES) ? 0 : c_slot + 1;
+			compute_stage<C, false>(acc, As + c_slot * C::A_STAGE, Bs + c_slot * C::B_STAGE, wm, wn, g, t);
+			c_slot = (c_slot + 1 == C::STAGES) ? 0 : c_slot + 1;
 		}
 #pragma unroll
-		for (int i = 0; i < 8; i++)
+		for (int i = 0; i < C::MI; i++)
 		{
 #pragma unroll
-			for (int j = 0; j < 4; j++)
+			for (int j = 0; j < C::NJ; j++)
 			{
 				rowsum[i] = fma(acc[i][j][0], acc[i][j][0], rowsum[i]);
 				rowsum[i] = fma(acc[i][j][1], acc[i][j][1], rowsum[i]);
@@ -220,23 +221,73 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) var_gemm_kernel(const double
 	}
 	cp_async_wait<0>();
 	__syncthreads();
-	// reduce over the 4 lanes of a quad (columns) and over the 4 column-warps
-	double* red = smem; // [4][128]
+	// reduce over the 4 lanes of a quad (columns) and over the column-warps
+	double* red = smem; // [WARPS_N][128]
 #pragma unroll
-	for (int i = 0; i < 8; i++)
+	for (int i = 0; i < C::MI; i++)
 	{
 		double s = rowsum[i];
 		s += __shfl_xor_sync(0xffffffffu, s, 1);
 		s += __shfl_xor_sync(0xffffffffu, s, 2);
 		if (t == 0)
 		{
-			red[wn * BM + wm * 64 + i * 8 + g] = s;
+			red[wn * BM + wm * C::WTM + i * 8 + g] = s;
 		}
 	}
 	__syncthreads();
 	if (tid < BM)
 	{
-		q[m0 + tid] = (red[tid] + red[BM + tid]) + (red[2 * BM + tid] + red[3 * BM + tid]);
+		double s = 0.0;
+#pragma unroll
+		for (int w = 0; w < C::WARPS_N; w++)
+		{
+			s += red[w * BM + tid];
+		}
+		q[m0 + tid] = s;
+	}
+}
+
+/// Tile configurations of the variance GEMM selectable at run time (tuned on the B200, see profiles/).
+using VarCfg0 = gemm::Config<16, 4, 2, 4>;
+using VarCfg1 = gemm::Config<32, 3, 2, 4>;
+using VarCfg2 = gemm::Config<16, 4, 4, 4>;
+using VarCfg3 = gemm::Config<32, 3, 4, 4>;
+using VarCfg4 = gemm::Config<16, 5, 2, 4>;
+using VarCfg5 = gemm::Config<16, 4, 2, 8>;
+using VarCfg6 = gemm::Config<16, 4, 4, 2>;
+constexpr int NUM_VAR_VARIANTS = 7;
+int g_var_variant = 1; // BK = 32, 3 stages, 2 x 4 warps: 88.8 % of the DMMA peak on B200 (profiles/r01_tune_var_gemm.txt)
+
+template <typename C>
+void launch_var_gemm_cfg(gple_ctx* ctx, const double* A, const double* W, int n, int rows, double* q)
+{
+	static bool attr_done = false;
+	if (!attr_done)
+	{
+		GPLE_CUDA(cudaFuncSetAttribute(var_gemm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM_BYTES)));
+		attr_done = true;
+	}
+	GPLE_LAUNCH(ctx, var_gemm_kernel<C>, rows / 128, C::THREADS, C::SMEM_BYTES, A, W, n, q);
+}
+
+void launch_var_gemm(gple_ctx* ctx, int variant, const double* A, const double* W, int n, int rows, double* q)
+{
+	switch (variant)
+	{
+	case 1:
+		return launch_var_gemm_cfg<VarCfg1>(ctx, A, W, n, rows, q);
+	case 2:
+		return launch_var_gemm_cfg<VarCfg2>(ctx, A, W, n, rows, q);
+	case 3:
+		return launch_var_gemm_cfg<VarCfg3>(ctx, A, W, n, rows, q);
+	case 4:
+		return launch_var_gemm_cfg<VarCfg4>(ctx, A, W, n, rows, q);
+	case 5:
+		return launch_var_gemm_cfg<VarCfg5>(ctx, A, W, n, rows, q);
+	case 6:
+		return launch_var_gemm_cfg<VarCfg6>(ctx, A, W, n, rows, q);
+	default:
+		return launch_var_gemm_cfg<VarCfg0>(ctx, A, W, n, rows, q);
 	}
 }
 
@@ -768,7 +819,6 @@ void gpr_setup_attributes()
 		return;
 	}
 	chol_setup_attributes();
-	GPLE_CUDA(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SMEM_BYTES)));
 	done = true;
 }
 
@@ -970,7 +1020,7 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		if (d_var != nullptr || d_cut != nullptr)
 		{
 			ProfScope prof(ctx, GPLE_PROF_VARIANCE_GEMM, double(rows) * n * (double(n) + 128.0), 1);
-			GPLE_LAUNCH(ctx, var_gemm_kernel, rows / 128, gemm::THREADS, gemm::SMEM_BYTES, A, m->W, n, q);
+			launch_var_gemm(ctx, g_var_variant, A, m->W, n, rows, q);
 		}
 		else
 		{
@@ -989,6 +1039,43 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 			GPLE_LAUNCH(ctx, sqerr_kernel, 1, 1024, 0, pred, rows, row0, total_rows, d_yq, nb, nb, m->rescale, d_err);
 		}
 	}
+}
+
+int set_variance_gemm_variant(int variant)
+{
+	if (variant < 0 || variant >= NUM_VAR_VARIANTS)
+	{
+		return -1;
+	}
+	g_var_variant = variant;
+	return 0;
+}
+
+/// Times `iters` launches of one variant on synthetic operands (tuning / roofline helper)
+double bench_variance_gemm(gple_ctx* ctx, int variant, int rows, int n, int iters)
+{
+	gpr_setup_attributes();
+	double* A = ctx->ws.get<double>("pred.A", size_t(rows) * n);
+	double* W = ctx->ws.get<double>("bench.W", size_t(n) * n);
+	double* q = ctx->ws.get<double>("pred.q", size_t(rows));
+	GPLE_CUDA(cudaMemsetAsync(A, 0, size_t(rows) * n * sizeof(double), ctx->stream));
+	GPLE_CUDA(cudaMemsetAsync(W, 0, size_t(n) * n * sizeof(double), ctx->stream));
+	launch_var_gemm(ctx, variant, A, W, n, rows, q);
+	cudaEvent_t e0, e1;
+	GPLE_CUDA(cudaEventCreate(&e0));
+	GPLE_CUDA(cudaEventCreate(&e1));
+	GPLE_CUDA(cudaEventRecord(e0, ctx->stream));
+	for (int i = 0; i < iters; i++)
+	{
+		launch_var_gemm(ctx, variant, A, W, n, rows, q);
+	}
+	GPLE_CUDA(cudaEventRecord(e1, ctx->stream));
+	GPLE_CUDA(cudaEventSynchronize(e1));
+	float ms = 0.f;
+	GPLE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	return double(ms) / iters;
 }
 
 void kernel_real_device(gple_ctx* ctx, const double* XL, int nL, const double* XR, int nR, const double* th, int same, double* K, double* dK)

@@ -11,6 +11,8 @@ int train_complex(gple_ctx* ctx, const double* X, const double* y, size_t N, con
 /// All pointers are device pointers.  d_pred / d_cut: 1 (real) or 2 (complex, interleaved) doubles per point;
 /// d_err accumulates the squared validation error against d_yq (same layout as d_pred); any output may be null.
 void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size_t Q, const double* d_yq, double* d_pred, double* d_var, double* d_cut, double* d_err);
+int set_variance_gemm_variant(int variant);
+double bench_variance_gemm(gple_ctx* ctx, int variant, int rows, int n, int iters);
 void kernel_real_device(gple_ctx* ctx, const double* XL, int nL, const double* XR, int nR, const double* theta, int same, double* K, double* dK);
 void kernel_complex_device(gple_ctx* ctx, const double* XL, int nL, const double* XR, int nR, const double* theta, int same, double* K, double* Kt);
 

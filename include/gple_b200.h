@@ -167,6 +167,10 @@ extern "C"
 	};
 	int gple_profile_enable(gple_ctx* ctx, int on);
 	int gple_profile_read(gple_ctx* ctx, int slot, double* total_ms, unsigned long long* launches, double* work);
+	/* Tile-configuration tuning of the variance GEMM: time `iters` launches of variant 0..6 on zero operands of
+	 * `rows` x n (both multiples of 128); gple_set_variance_gemm_variant selects the variant used by predictions. */
+	int gple_tune_variance_gemm(gple_ctx* ctx, int variant, int rows, int n, int iters, double* ms_per_launch);
+	int gple_set_variance_gemm_variant(int variant);
 	/* Register-resident DMMA / DFMA loops: measured FP64 tensor and vector peaks of this GPU, in TFLOP/s. */
 	int gple_measure_fp64_peak(gple_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
 
