@@ -73,3 +73,23 @@ def test_prediction_parity(ck, oracle):
     scale = np.abs(r["cutoff"]).max()
     assert np.abs(p.get_cutoff_prediction() - r["cutoff"])[sharp].max() <= 1e-8 * scale
     assert np.abs(p.get_cutoff_prediction() - r["cutoff"]).max() <= 1e-5 * scale
+
+
+def test_gradients_parity(ck, oracle):
+    """complex_kernel.cpp:379-590 and :648-667 (incl. quirks q2, q10) evaluated in composite form on the GPU."""
+    X, y = syn.training_set(4, 1, 150)
+    k = ck.TrainingComplexKernel(THETA, (X, y), True, True, True)
+    o = oracle.TrainingComplexKernel(THETA, X, y, True, True, True)
+    assert np.abs(k.get_error_derivative() - o.derror).max() <= 1e-7 * np.abs(o.derror).max()
+    assert np.abs(k.get_purity_derivative() - o.dpurity).max() <= 1e-7 * np.abs(o.dpurity).max()
+    Xq, yq = syn.extra_points(4, 1, X, 600)
+    p = ck.PredictiveComplexKernel(Xq, k, True, yq)
+    r = o.predict(Xq, yq, True)
+    assert p.get_error() == pytest.approx(r["error"], rel=1e-8)
+    assert np.abs(p.get_error_derivative() - r["derror"]).max() <= 1e-6 * np.abs(r["derror"]).max()
+    from gaussian_process_liouville_equation_b200 import dynamics
+
+    val, g = dynamics.loose_function(THETA, (X, y), (Xq, yq), grad=True)
+    vo, go = oracle.loose_function(THETA, X, y, Xq, yq, grad=True)
+    assert val == pytest.approx(vo, rel=1e-8)
+    assert np.abs(g - go).max() <= 1e-6 * np.abs(go).max()
