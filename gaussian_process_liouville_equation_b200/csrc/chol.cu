@@ -45,10 +45,23 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
 		double s = 0.0;
 		if (i >= j)
 		{
-			for (int k = q; k < j; k += 4)
+			// 4 independent partial sums so that the shared-memory loads pipeline (the loop is latency-bound otherwise)
+			double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+			const double* ri = S + i * LP;
+			const double* rj = S + j * LP;
+			int k = q;
+			for (; k + 12 < j; k += 16)
 			{
-				s += S[i * LP + k] * S[j * LP + k];
+				s = fma(ri[k], rj[k], s);
+				s1 = fma(ri[k + 4], rj[k + 4], s1);
+				s2 = fma(ri[k + 8], rj[k + 8], s2);
+				s3 = fma(ri[k + 12], rj[k + 12], s3);
 			}
+			for (; k < j; k += 4)
+			{
+				s = fma(ri[k], rj[k], s);
+			}
+			s = (s + s1) + (s2 + s3);
 		}
 		s += __shfl_xor_sync(0xffffffffu, s, 1);
 		s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -94,10 +107,22 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
 			double s = 0.0;
 			if (r > c)
 			{
-				for (int k = c + q; k < r; k += 4)
+				double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+				const double* lr = S + r * LP;
+				const double* xc = S + c * LP + 1;
+				int k = c + q;
+				for (; k + 12 < r; k += 16)
 				{
-					s += S[r * LP + k] * S[c * LP + k + 1];
+					s = fma(lr[k], xc[k], s);
+					s1 = fma(lr[k + 4], xc[k + 4], s1);
+					s2 = fma(lr[k + 8], xc[k + 8], s2);
+					s3 = fma(lr[k + 12], xc[k + 12], s3);
 				}
+				for (; k < r; k += 4)
+				{
+					s = fma(lr[k], xc[k], s);
+				}
+				s = (s + s1) + (s2 + s3);
 			}
 			s += __shfl_xor_sync(0xffffffffu, s, 1);
 			s += __shfl_xor_sync(0xffffffffu, s, 2);

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 /// (flattened (n-tile, k-step) sequence) so the tensor pipe never drains.  The squared accumulators are
 /// folded into per-thread row sums; no Z is ever written.
 template <typename C>
-__global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* __restrict__ A, const double* __restrict__ W, const int n, double* __restrict__ q)
+__global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* __restrict__ A, const double* __restrict__ W, const int n, double* __restrict__ q, const int rows)
 {
 	using namespace gemm;
 	extern __shared__ __align__(16) double smem[];
@@ -166,8 +166,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 	const int m0 = blockIdx.x * BM;
 	const int T = n / BN;
 	const double* Ag = A + size_t(m0) * n;
+	// When a chunk has fewer than ~148 row blocks the n-tiles are dealt round-robin to gridDim.y CTAs per row
+	// block (interleaving balances the triangular work); each writes its partial row sums to q[blockIdx.y][rows].
+	const int nt0 = blockIdx.y, nts = gridDim.y;
 
-	int l_nt = 0, l_kt = 0, l_slot = 0;
+	int l_nt = nt0, l_kt = 0, l_slot = 0;
 	auto issue = [&]()
 	{
 		if (l_nt < T)
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 			if (++l_kt == (l_nt + 1) * (BN / C::BK))
 			{
 				l_kt = 0;
-				l_nt++;
+				l_nt += nts;
 			}
 		}
 		cp_async_commit();
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 	}
 	double acc[C::MI][C::NJ][2];
 	int c_slot = 0;
-	for (int nt = 0; nt < T; nt++)
+	for (int nt = nt0; nt < T; nt += nts)
 	{
 		zero_acc<C>(acc);
 		const int steps = (nt + 1) * (BN / C::BK);
@@ -243,8 +246,24 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 		{
 			s += red[w * BM + tid];
 		}
-		q[m0 + tid] = s;
+		q[size_t(blockIdx.y) * rows + m0 + tid] = s;
 	}
+}
+
+/// q[r] = sum over the n-splits of the partial row sums
+__global__ void var_reduce_kernel(double* __restrict__ q, const int rows, const int splits)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= rows)
+	{
+		return;
+	}
+	double s = q[r];
+	for (int k = 1; k < splits; k++)
+	{
+		s += q[size_t(k) * rows + r];
+	}
+	q[r] = s;
 }
 
 /// Tile configurations of the variance GEMM selectable at run time (tuned on the B200, see profiles/).
@@ -256,6 +275,7 @@ using VarCfg4 = gemm::Config<16, 5, 2, 4>;
 using VarCfg5 = gemm::Config<16, 4, 2, 8>;
 using VarCfg6 = gemm::Config<16, 4, 4, 2>;
 constexpr int NUM_VAR_VARIANTS = 7;
+constexpr int MAX_VAR_SPLITS = 16;
 int g_var_variant = 1; // BK = 32, 3 stages, 2 x 4 warps: 88.8 % of the DMMA peak on B200 (profiles/r01_tune_var_gemm.txt)
 
 template <typename C>
@@ -267,7 +287,24 @@ void launch_var_gemm_cfg(gple_ctx* ctx, const double* A, const double* W, int n,
 		GPLE_CUDA(cudaFuncSetAttribute(var_gemm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM_BYTES)));
 		attr_done = true;
 	}
-	GPLE_LAUNCH(ctx, var_gemm_kernel<C>, rows / 128, C::THREADS, C::SMEM_BYTES, A, W, n, q);
+	// choose the number of n-splits S that minimises the makespan ceil(blocks * S / SMs) / S
+	const int mb = rows / 128, T = n / 128;
+	int best = 1;
+	double best_cost = double((mb + ctx->num_sms - 1) / ctx->num_sms);
+	for (int S = 2; S <= std::min(T, MAX_VAR_SPLITS); S++)
+	{
+		const double cost = double((mb * S + ctx->num_sms - 1) / ctx->num_sms) / S * (1.0 + 0.01 * S); // small penalty per split
+		if (cost < best_cost * 0.97)
+		{
+			best_cost = cost;
+			best = S;
+		}
+	}
+	GPLE_LAUNCH(ctx, var_gemm_kernel<C>, dim3(mb, best), C::THREADS, C::SMEM_BYTES, A, W, n, q, rows);
+	if (best > 1)
+	{
+		GPLE_LAUNCH(ctx, var_reduce_kernel, (rows + 255) / 256, 256, 0, q, rows, best);
+	}
 }
 
 void launch_var_gemm(gple_ctx* ctx, int variant, const double* A, const double* W, int n, int rows, double* q)
@@ -828,9 +865,10 @@ void free_model(gple_ctx* ctx, gple_model* m)
 	{
 		return;
 	}
+	gple_ctx* owner = m->owner != nullptr ? m->owner : ctx;
 	for (double* p : {m->X, m->W, m->v, m->label, m->kinv_diag, m->Kinv, m->dv})
 	{
-		ctx->pool.free(p); // stream-ordered reuse: every consumer runs on ctx->stream
+		owner->pool.free(p); // reuse is ordered on the owner's stream; callers sync before handing a model to another context
 	}
 	delete m;
 }
@@ -862,6 +900,7 @@ int train_real(gple_ctx* ctx, const double* X_, const double* y_, size_t N, cons
 	gpr_setup_attributes();
 	DeviceArray<double> X(ctx, X_, 2 * N, false), y(ctx, y_, 2 * N, false);
 	gple_model* m = new gple_model();
+	m->owner = ctx;
 	m->is_complex = 0;
 	m->N = N;
 	m->Np = int(round_up(N, 128));
@@ -928,6 +967,7 @@ int train_complex(gple_ctx* ctx, const double* X_, const double* y_, size_t N, c
 	gpr_setup_attributes();
 	DeviceArray<double> X(ctx, X_, 2 * N, false), y(ctx, y_, 2 * N, false);
 	gple_model* m = new gple_model();
+	m->owner = ctx;
 	m->is_complex = 1;
 	m->N = N;
 	m->Np = int(round_up(N, 128));
@@ -1004,7 +1044,7 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 	const int max_rows = int(std::min<long long>(CHUNK_ROWS, (long long)round_up(size_t(total_rows), 128)));
 	double* A = ctx->ws.get<double>("pred.A", size_t(max_rows) * n);
 	double* pred = ctx->ws.get<double>("pred.f", size_t(max_rows));
-	double* q = ctx->ws.get<double>("pred.q", size_t(max_rows));
+	double* q = ctx->ws.get<double>("pred.q", size_t(max_rows) * MAX_VAR_SPLITS);
 	if (d_err != nullptr)
 	{
 		GPLE_CUDA(cudaMemsetAsync(d_err, 0, sizeof(double), ctx->stream));
@@ -1057,7 +1097,7 @@ double bench_variance_gemm(gple_ctx* ctx, int variant, int rows, int n, int iter
 	gpr_setup_attributes();
 	double* A = ctx->ws.get<double>("pred.A", size_t(rows) * n);
 	double* W = ctx->ws.get<double>("bench.W", size_t(n) * n);
-	double* q = ctx->ws.get<double>("pred.q", size_t(rows));
+	double* q = ctx->ws.get<double>("pred.q", size_t(rows) * MAX_VAR_SPLITS);
 	GPLE_CUDA(cudaMemsetAsync(A, 0, size_t(rows) * n * sizeof(double), ctx->stream));
 	GPLE_CUDA(cudaMemsetAsync(W, 0, size_t(n) * n * sizeof(double), ctx->stream));
 	launch_var_gemm(ctx, variant, A, W, n, rows, q);

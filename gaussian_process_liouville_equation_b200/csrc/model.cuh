@@ -4,6 +4,7 @@
 
 struct gple_model
 {
+	gple_ctx* owner = nullptr; // context whose buffer pool the device buffers came from
 	int is_complex = 0;
 	size_t N = 0;	// training points
 	int Np = 0;		// N padded to a multiple of 128

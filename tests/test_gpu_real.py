@@ -155,3 +155,44 @@ def test_not_spd_is_reported(gk):
     X[1] = X[0]
     k = gk.TrainingKernel(np.array([1.0, 0.7, 0.7, 0.0]), (X, y), True, True, False)
     assert k.status == 2 and np.isnan(k.get_error())
+
+
+def test_chunk_boundaries_and_batch_invariance(gk, oracle):
+    """Predictions are independent of where a point falls in the batch: across the 18944-row chunk boundary, in the
+    n-split tail chunk (partial row block), and as a single-point call."""
+    X, y = syn.training_set(8, 0, 260)
+    th = syn.theta_real()
+    k = gk.TrainingKernel(th, (X, y))
+    Q = 148 * 128 + 57
+    Xq, _ = syn.extra_points(8, 0, X, Q)
+    p = gk.PredictiveKernel(Xq, k)
+    idx = np.array([0, 1, 127, 128, 9471, 18943, 18944, 18945, Q - 1])
+    sub = gk.PredictiveKernel(Xq[idx], k)
+    assert np.array_equal(p.get_prediction()[idx], sub.get_prediction())
+    assert np.abs(p.get_variance()[idx] - sub.get_variance()).max() <= 1e-13 * th[0] ** 2
+    for i in (18943, 18944, Q - 1):
+        one = gk.PredictiveKernel(Xq[i], k)
+        assert one.get_prediction()[0] == p.get_prediction()[i]
+        assert abs(one.get_variance()[0] - p.get_variance()[i]) <= 1e-13
+    o = oracle.TrainingKernel(th, X, y).predict(Xq[idx])
+    assert np.abs(p.get_prediction()[idx] - o["pred"]).max() <= 1e-9 * np.abs(o["pred"]).max()
+    assert np.abs(p.get_variance()[idx] - o["var"]).max() <= 1e-9 * th[0] ** 2
+
+
+def test_argument_errors_are_status_codes(gk):
+    from gaussian_process_liouville_equation_b200 import _lib as L
+
+    ctx = L.default_context()
+    import ctypes as C
+
+    h, s = C.c_void_p(), L.RealScalars()
+    th = syn.theta_real()
+    X, y = syn.training_set(1, 0, 8)
+    yv = np.ascontiguousarray(y).view(np.float64)
+    assert ctx.lib.gple_train_real(ctx.h, L.addr(X), L.addr(yv), 0, L.addr(th), 3, C.byref(h), C.byref(s)) == L.ERR_ARG  # empty training set
+    assert ctx.lib.gple_train_real(ctx.h, None, L.addr(yv), 8, L.addr(th), 3, C.byref(h), C.byref(s)) == L.ERR_ARG
+    k = gk.TrainingKernel(th, (X, y))
+    out = np.empty(4)
+    assert ctx.lib.gple_predict_complex(ctx.h, k.h, L.addr(X), 2, None, L.addr(out), None, None, None, None) == L.ERR_ARG  # wrong kind
+    assert ctx.lib.gple_predict_real(ctx.h, k.h, L.addr(X), 0, None, L.addr(out), None, None, None, None) == L.ERR_ARG  # no query
+    assert b"model kind" in ctx.lib.gple_last_error(ctx.h) or b"query" in ctx.lib.gple_last_error(ctx.h)
