@@ -185,14 +185,33 @@ void run_gemm(gple_ctx* ctx, bool b_nn, const gemm::GemmArgs& a)
 	{
 		return;
 	}
-	const dim3 grid(a.N / gemm::BN, a.M / gemm::BM);
-	if (b_nn)
+	// 128 x 128 tiles once they fill at least about half of the SMs, 64 x 64 tiles below that (latency-bound regime)
+	const long long tiles128 = (long long)(a.N / 128) * (a.M / 128) / (a.lower_only ? 2 : 1);
+	if (tiles128 * 2 >= ctx->num_sms || a.in_place)
 	{
-		GPLE_LAUNCH(ctx, (gemm::gemm_kernel<gemm::DefaultConfig, true>), grid, gemm::DefaultConfig::THREADS, gemm::DefaultConfig::SMEM_BYTES, a);
+		using C = gemm::DefaultConfig;
+		const dim3 grid(a.N / C::BN, a.M / C::BM);
+		if (b_nn)
+		{
+			GPLE_LAUNCH(ctx, (gemm::gemm_kernel<C, true>), grid, C::THREADS, C::SMEM_BYTES, a);
+		}
+		else
+		{
+			GPLE_LAUNCH(ctx, (gemm::gemm_kernel<C, false>), grid, C::THREADS, C::SMEM_BYTES, a);
+		}
 	}
 	else
 	{
-		GPLE_LAUNCH(ctx, (gemm::gemm_kernel<gemm::DefaultConfig, false>), grid, gemm::DefaultConfig::THREADS, gemm::DefaultConfig::SMEM_BYTES, a);
+		using C = gemm::SmallConfig;
+		const dim3 grid(a.N / C::BN, a.M / C::BM);
+		if (b_nn)
+		{
+			GPLE_LAUNCH(ctx, (gemm::gemm_kernel<C, true>), grid, C::THREADS, C::SMEM_BYTES, a);
+		}
+		else
+		{
+			GPLE_LAUNCH(ctx, (gemm::gemm_kernel<C, false>), grid, C::THREADS, C::SMEM_BYTES, a);
+		}
 	}
 }
 
@@ -229,6 +248,7 @@ struct Chol
 			g.alpha = 1.0;
 			g.beta = 0.0;
 			g.tri = gemm::B_LOWER_NT;
+			g.in_place = 1;
 			run_gemm(ctx, false, g); // in place: one n-tile per row block, all reads precede the epilogue
 			return;
 		}
@@ -326,6 +346,8 @@ void chol_setup_attributes()
 	}
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::DefaultConfig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::DefaultConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::DefaultConfig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::DefaultConfig::SMEM_BYTES)));
+	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::SmallConfig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SmallConfig::SMEM_BYTES)));
+	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::SmallConfig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SmallConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LEAF_SMEM)));
 	done = true;
 }

@@ -19,12 +19,11 @@ namespace gple
 {
 namespace gemm
 {
-constexpr int BM = 128, BN = 128;
-
-/// Tile configuration.  BK_ in {16, 32}; warp tile = (128 / WARPS_M_) x (128 / WARPS_N_).
-template <int BK_, int STAGES_, int WARPS_M_, int WARPS_N_>
+/// Tile configuration.  CTA tile BM_ x BN_ x BK_ (BK_ in {16, 32}); warp tile = (BM / WARPS_M_) x (BN / WARPS_N_).
+template <int BK_, int STAGES_, int WARPS_M_, int WARPS_N_, int BM_ = 128, int BN_ = 128>
 struct Config
 {
+	static constexpr int BM = BM_, BN = BN_;
 	static constexpr int BK = BK_, STAGES = STAGES_, WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;
 	static constexpr int THREADS = WARPS_M * WARPS_N * 32;
 	static constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N; // warp tile
@@ -37,8 +36,11 @@ struct Config
 	static constexpr size_t SMEM_BYTES = size_t(STAGES) * (A_STAGE + B_STAGE) * sizeof(double);
 	static_assert(KP % 16 == 4 && NP % 16 == 4, "pitch must be 4 mod 16 doubles for conflict-free fragment loads");
 };
-/// general GEMMs (Cholesky / inverse / gradients)
+/// general GEMMs (Cholesky / inverse / gradients): 128 x 128 tiles when the grid fills the chip ...
 using DefaultConfig = Config<16, 4, 2, 4>;
+/// ... and 64 x 64 tiles (4 warps, 4x more CTAs, 4x shorter per-tile latency) for the small, latency-bound
+/// GEMMs on the critical path of the recursive factorisation
+using SmallConfig = Config<16, 4, 2, 2, 64, 64>;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
@@ -61,28 +63,29 @@ __device__ __forceinline__ void dmma884(double (&c)[2], const double a, const do
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-/// Copy a K-contiguous 128 x BK tile of a row-major matrix into [128][KP].
-template <typename C>
+/// Copy a K-contiguous ROWS x BK tile of a row-major matrix into [ROWS][KP].
+template <typename C, int ROWS>
 __device__ __forceinline__ void load_tile_kmajor(double* s, const double* __restrict__ g, const size_t ld, const int tid)
 {
 	constexpr int CH = C::BK / 2; // 16-byte chunks per row
 #pragma unroll
-	for (int i = 0; i < (128 * CH) / C::THREADS; i++)
+	for (int i = 0; i < (ROWS * CH) / C::THREADS; i++)
 	{
 		const int c = tid + i * C::THREADS;
 		const int row = c / CH, ch = c % CH;
 		cp_async16(s + row * C::KP + ch * 2, g + size_t(row) * ld + ch * 2);
 	}
 }
-/// Copy an N-contiguous BK x 128 tile (k rows) into [BK][NP].
+/// Copy an N-contiguous BK x BN tile (k rows) into [BK][NP].
 template <typename C>
 __device__ __forceinline__ void load_tile_nmajor(double* s, const double* __restrict__ g, const size_t ld, const int tid)
 {
+	constexpr int CH = C::BN / 2;
 #pragma unroll
-	for (int i = 0; i < (C::BK * 64) / C::THREADS; i++)
+	for (int i = 0; i < (C::BK * CH) / C::THREADS; i++)
 	{
 		const int c = tid + i * C::THREADS;
-		const int row = c >> 6, ch = c & 63;
+		const int row = c / CH, ch = c % CH;
 		cp_async16(s + row * C::NP + ch * 2, g + size_t(row) * ld + ch * 2);
 	}
 }
@@ -156,10 +159,11 @@ struct GemmArgs
 	const double* B;
 	double* C;
 	size_t lda, ldb, ldc;
-	int M, N, K; // multiples of 128
+	int M, N, K; // multiples of 128 (tiles of 128 or 64)
 	double alpha, beta;
 	int tri;		// bitmask of Tri
 	int lower_only; // skip output tiles strictly above the diagonal (SYRK-style)
+	int in_place;	// C aliases A with N == 128: one CTA must own a whole row strip (forces the 128 x 128 tiling)
 };
 
 /// C = beta * C + alpha * A * op(B)
@@ -169,6 +173,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const GemmArgs p)
 	extern __shared__ __align__(16) double smem[];
 	double* As = smem;
 	double* Bs = smem + C::STAGES * C::A_STAGE;
+	constexpr int BM = C::BM, BN = C::BN;
 	const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
 	if (p.lower_only && n0 > m0)
 	{
@@ -209,14 +214,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const GemmArgs p)
 		if (kt < nk)
 		{
 			const int slot = kt % C::STAGES;
-			load_tile_kmajor<C>(As + slot * C::A_STAGE, Ag + size_t(kt) * C::BK, p.lda, tid);
+			load_tile_kmajor<C, C::BM>(As + slot * C::A_STAGE, Ag + size_t(kt) * C::BK, p.lda, tid);
 			if (B_NN)
 			{
 				load_tile_nmajor<C>(Bs + slot * C::B_STAGE, Bg + size_t(kt) * C::BK * p.ldb, p.ldb, tid);
 			}
 			else
 			{
-				load_tile_kmajor<C>(Bs + slot * C::B_STAGE, Bg + size_t(kt) * C::BK, p.ldb, tid);
+				load_tile_kmajor<C, C::BN>(Bs + slot * C::B_STAGE, Bg + size_t(kt) * C::BK, p.ldb, tid);
 			}
 		}
 		cp_async_commit();

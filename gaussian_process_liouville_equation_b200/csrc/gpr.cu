@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 	double* Bs = smem + C::STAGES * C::A_STAGE;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N, g = lane >> 2, t = lane & 3;
+	constexpr int BM = 128, BN = 128;
+	static_assert(C::BM == 128 && C::BN == 128, "the variance GEMM walks 128-wide n-tiles");
 	const int m0 = blockIdx.x * BM;
 	const int T = n / BN;
 	const double* Ag = A + size_t(m0) * n;
@@ -175,8 +177,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 	{
 		if (l_nt < T)
 		{
-			load_tile_kmajor<C>(As + l_slot * C::A_STAGE, Ag + size_t(l_kt) * C::BK, size_t(n), tid);
-			load_tile_kmajor<C>(Bs + l_slot * C::B_STAGE, W + size_t(l_nt) * BN * n + size_t(l_kt) * C::BK, size_t(n), tid);
+			load_tile_kmajor<C, 128>(As + l_slot * C::A_STAGE, Ag + size_t(l_kt) * C::BK, size_t(n), tid);
+			load_tile_kmajor<C, 128>(Bs + l_slot * C::B_STAGE, W + size_t(l_nt) * BN * n + size_t(l_kt) * C::BK, size_t(n), tid);
 			l_slot = (l_slot + 1 == C::STAGES) ? 0 : l_slot + 1;
 			if (++l_kt == (l_nt + 1) * (BN / C::BK))
 			{
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(128) col_pass_kernel(const double* __restrict_
 	const int i_begin = max(blockIdx.y * slab, (k / 128) * 128), i_end = min(n, (blockIdx.y + 1) * slab);
 	double sv = 0.0, ss = 0.0, sc = 0.0;
 	const bool cross = want_cross && k < Np;
-#pragma unroll 4
+#pragma unroll 8
 	for (int i = i_begin; i < i_end; i++)
 	{
 		const double a = W[size_t(i) * n + k];
@@ -821,7 +823,8 @@ int train_common(gple_ctx* ctx, gple_model* m, const BlockSpec& spec, const Devi
 	GPLE_LAUNCH(ctx, label_kernel, 1, 1024, 0, reinterpret_cast<const double2*>(y.dev), N, Np, m->is_complex, m->label, d_scal);
 	double* z = ctx->ws.get<double>("train.z", size_t(n));
 	GPLE_LAUNCH(ctx, trmv_lower_kernel, (n + 7) / 8, 256, 0, m->W, n, m->label, z);
-	const int slabs = std::max(1, std::min(64, n / 512));
+	// row slabs of 128 (capped at 64 slabs): enough CTAs in flight to cover the load latency of this O(n^2) pass
+	const int slabs = std::max(1, std::min(64, n / 128));
 	const int slab = int(round_up(size_t((n + slabs - 1) / slabs), 128));
 	const int nslab = (n + slab - 1) / slab;
 	double* part = ctx->ws.get<double>("train.colpart", size_t(nslab) * 3 * n);
