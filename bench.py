@@ -258,6 +258,7 @@ def run_ours(args):
         resident()
     torch.cuda.synchronize()
     dmma_peak, dfma_peak = ctx.fp64_peak()
+    tile_peak = ctx.dmma_tile_peak()
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -309,7 +310,8 @@ def run_ours(args):
                      "peak_source": "measured live by gple_measure_fp64_peak (register-resident DMMA.8x8x4 loop); MEASURED_PEAKS.json has no FP64 entry",
                      "launches": var_n, "avg_launch_ms": var_ms / max(var_n, 1), "share_of_step": var_ms / total_ms,
                      "flops_counted": "executed (triangular) flops rows*n*(n+128); the reference formulation K* K^-1 k^T would be 2x"},
-        "extra": {"fp64_dfma_peak_tflops": dfma_peak,
+        "extra": {"fp64_dfma_peak_tflops": dfma_peak, "dmma_register_tile_ceiling_tflops": tile_peak,
+                  "dmma_register_tile_ceiling_note": "same 8x4 DMMA register tile at 8 warps/SM with changing operands and no memory traffic: the ceiling of an mma.sync FP64 GEMM at this occupancy",
                   "kernel_build_gbs": kb_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else None, "kernel_build_share": kb_ms / total_ms,
                   "cholesky_inverse_tflops": fa_flops / (fa_ms * 1e-3) / 1e12 if fa_ms > 0 else None, "factorise_share": fa_ms / total_ms,
                   "reference_formulation_tflops_equiv": alg_flops_step / (ms_per_step * 1e-3) / 1e12,

@@ -62,6 +62,7 @@ SIGNATURES = {
     "gple_set_variance_gemm_variant": (C.c_int, [C.c_int]),
     "gple_profile_enable": (C.c_int, [_vp, C.c_int]),
     "gple_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
+    "gple_measure_dmma_tile_peak": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "gple_measure_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
@@ -152,6 +153,11 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self.check(self.lib.gple_measure_fp64_peak(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def dmma_tile_peak(self) -> float:
+        a = C.c_double()
+        self.check(self.lib.gple_measure_dmma_tile_peak(self.h, C.byref(a)))
+        return a.value
 
     def close(self):
         if getattr(self, "h", None):

@@ -83,6 +83,63 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, const int i
 		out[0] = s;
 	}
 }
+/// Same DMMA stream as the GEMM inner loop (8 x 4 register tile: 32 accumulators, 8 distinct A and 4 distinct B
+/// operands per k-step, no memory traffic at all): the ceiling of a register-tiled mma.sync FP64 kernel.
+__global__ void __launch_bounds__(256, 1) dmma_tile_peak_kernel(double* out, const int iters)
+{
+	double acc[8][4][2];
+#pragma unroll
+	for (int i = 0; i < 8; i++)
+	{
+#pragma unroll
+		for (int j = 0; j < 4; j++)
+		{
+			acc[i][j][0] = acc[i][j][1] = 0.0;
+		}
+	}
+	double a[8], b[4];
+#pragma unroll
+	for (int i = 0; i < 8; i++)
+	{
+		a[i] = 1.0 + (threadIdx.x + i) * 1e-9;
+	}
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+	{
+		b[j] = 1.0 - (threadIdx.x + j) * 1e-9;
+	}
+	for (int it = 0; it < iters; it++)
+	{
+#pragma unroll
+		for (int i = 0; i < 8; i++)
+		{
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+			{
+				gemm::dmma884(acc[i][j], a[i], b[j]);
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < 8; i++)
+		{
+			a[i] += 1e-12; // operands change every k-step, as in a real GEMM
+		}
+	}
+	double s = 0.0;
+#pragma unroll
+	for (int i = 0; i < 8; i++)
+	{
+#pragma unroll
+		for (int j = 0; j < 4; j++)
+		{
+			s += acc[i][j][0] + acc[i][j][1];
+		}
+	}
+	if (s == 12345.678)
+	{
+		out[0] = s;
+	}
+}
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, const int iters)
 {
 	double acc[16];
@@ -641,6 +698,37 @@ extern "C"
 				}
 				p.launches = 0;
 				p.work = 0.0;
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_measure_dmma_tile_peak(gple_ctx* ctx, double* tflops)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(tflops != nullptr, "gple_measure_dmma_tile_peak: null argument");
+				double* d = ctx->ws.get<double>("peak.out", 8);
+				const int iters = 2048, blocks = ctx->num_sms;
+				cudaEvent_t e0, e1;
+				GPLE_CUDA(cudaEventCreate(&e0));
+				GPLE_CUDA(cudaEventCreate(&e1));
+				double best = 0.0;
+				for (int rep = 0; rep < 4; rep++)
+				{
+					float ms = 0.f;
+					GPLE_CUDA(cudaEventRecord(e0, ctx->stream));
+					GPLE_LAUNCH(ctx, dmma_tile_peak_kernel, blocks, 256, 0, d, iters);
+					GPLE_CUDA(cudaEventRecord(e1, ctx->stream));
+					GPLE_CUDA(cudaEventSynchronize(e1));
+					GPLE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+					best = std::max(best, double(blocks) * 8 * 32 * iters * 512.0 / (ms * 1e-3) / 1e12);
+				}
+				cudaEventDestroy(e0);
+				cudaEventDestroy(e1);
+				*tflops = best;
 				return GPLE_OK;
 			}
 		);

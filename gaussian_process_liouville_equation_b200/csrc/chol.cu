@@ -17,135 +17,284 @@ namespace gple
 namespace
 {
 constexpr int LEAF = 128;
-constexpr int LP = 132;			 // pitch (doubles): 4 (mod 16) -> conflict-free for the (row, q) thread layout
-constexpr int LEAF_THREADS = 512; // 4 threads per row / column
-constexpr size_t LEAF_SMEM = (size_t(LEAF) * LP + LEAF) * sizeof(double);
+constexpr int LP = 132;			 // pitch (doubles): 4 (mod 16) -> conflict-free DMMA fragment loads
+constexpr int LEAF_THREADS = 256; // 8 warps
+constexpr int PW = 16;			 // panel width / inverse block size
+constexpr size_t LEAF_SMEM = (size_t(LEAF) * LP + 8 * 16 * 20) * sizeof(double);
 
-/// Factor one 128 x 128 diagonal block in shared memory (left-looking Cholesky-Crout, 4 lanes per row)
-/// and invert the resulting triangle (4 lanes per column).  L overwrites the block (upper part zeroed),
-/// its inverse goes to `dinv` (row-major 128 x 128, upper part zero).
+/// Factor one 128 x 128 diagonal block and invert the resulting triangle, entirely in shared memory.
+///   factor : right-looking with 16-wide panels -- the 16 x 16 diagonal block by one warp (registers + shuffles),
+///            the panel below by one independent row-wise triangular solve per thread (no barriers inside), and the
+///            rank-16 trailing update of the lower triangle by all warps on DMMA;
+///   inverse: X = L^-1 by 16 x 16 blocks -- diagonal blocks by forward substitution (16 lanes each), then block
+///            sub-diagonal after sub-diagonal  X_ij = -X_ii sum_{k=j}^{i-1} L_ik X_kj  on DMMA, one warp per block.
+/// L lives in the lower triangle of S (row-major, pitch LP); X is kept TRANSPOSED in the strictly-upper part,
+/// shifted by one column: X[a][b] (a >= b) = S[b][a + 1].
+/// L overwrites the block (upper part zeroed); its inverse goes to `dinv` (row-major 128 x 128, upper part zero).
 __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __restrict__ A, const size_t ld, double* __restrict__ dinv, int* __restrict__ info, const int global_row0)
 {
 	extern __shared__ __align__(16) double sm[];
-	double* S = sm;				  // [128][LP]: strictly-lower part = L; XT(c, i) = S[c][i + 1] (i >= c) = inverse, transposed
-	double* dg = sm + LEAF * LP; // diagonal of L
-	const int tid = threadIdx.x;
-	for (int e = tid; e < LEAF * LEAF; e += LEAF_THREADS)
+	double* S = sm;					 // [128][LP]
+	double* scratch = sm + LEAF * LP; // [8 warps][16][20]
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+	for (int e = tid; e < LEAF * LEAF / 2; e += LEAF_THREADS)
 	{
-		const int r = e >> 7, c = e & 127;
-		if (c <= r)
+		const int r = e >> 6, c2 = (e & 63) * 2;
+		if (c2 <= r)
 		{
-			S[r * LP + c] = A[size_t(r) * ld + c];
+			*reinterpret_cast<double2*>(S + r * LP + c2) = *reinterpret_cast<const double2*>(A + size_t(r) * ld + c2);
 		}
 	}
 	__syncthreads();
-	const int i = tid >> 2, q = tid & 3;
-	for (int j = 0; j < LEAF; j++)
+
+	// ---------------------------------------------------------------- factor
+	for (int p = 0; p < LEAF / PW; p++)
 	{
-		double s = 0.0;
-		if (i >= j)
+		const int c0 = p * PW;
+		if (warp == 0)
 		{
-			// 4 independent partial sums so that the shared-memory loads pipeline (the loop is latency-bound otherwise)
-			double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-			const double* ri = S + i * LP;
-			const double* rj = S + j * LP;
-			int k = q;
-			for (; k + 12 < j; k += 16)
+			// 16 x 16 diagonal block: lane i (< 16) owns row i in registers
+			const int i = lane & 15;
+			double a[PW];
+#pragma unroll
+			for (int k = 0; k < PW; k++)
 			{
-				s = fma(ri[k], rj[k], s);
-				s1 = fma(ri[k + 4], rj[k + 4], s1);
-				s2 = fma(ri[k + 8], rj[k + 8], s2);
-				s3 = fma(ri[k + 12], rj[k + 12], s3);
+				a[k] = (k <= i) ? S[(c0 + i) * LP + c0 + k] : 0.0;
 			}
-			for (; k < j; k += 4)
+#pragma unroll
+			for (int j = 0; j < PW; j++)
 			{
-				s = fma(ri[k], rj[k], s);
+				double d = __shfl_sync(0xffffffffu, a[j], j);
+				if (!(d > 0.0))
+				{
+					if (lane == 0)
+					{
+						atomicCAS(info, 0, global_row0 + c0 + j + 1);
+					}
+					d = 1.0;
+				}
+				const double rs = rsqrt(d), sd = d * rs; // one reciprocal square root instead of sqrt + division
+				const double l = (i == j) ? sd : a[j] * rs; // column j of L (rows >= j)
+				a[j] = l;
+#pragma unroll
+				for (int k = j + 1; k < PW; k++)
+				{
+					const double lk = __shfl_sync(0xffffffffu, l, k); // L[k][j]
+					if (i >= k)
+					{
+						a[k] = fma(-l, lk, a[k]);
+					}
+				}
 			}
-			s = (s + s1) + (s2 + s3);
-		}
-		s += __shfl_xor_sync(0xffffffffu, s, 1);
-		s += __shfl_xor_sync(0xffffffffu, s, 2);
-		if (i >= j && q == 0)
-		{
-			S[i * LP + j] -= s; // column j is only read as S[.][k], k < j, by the dot products: no hazard
+			if (lane < PW)
+			{
+#pragma unroll
+				for (int k = 0; k < PW; k++)
+				{
+					if (k <= i)
+					{
+						S[(c0 + i) * LP + c0 + k] = a[k];
+					}
+				}
+			}
 		}
 		__syncthreads();
-		double d = S[j * LP + j];
-		if (!(d > 0.0))
+		// panel below the diagonal block: row r solves x L_d^T = a (forward substitution, L_d broadcast from smem)
 		{
-			if (tid == 0)
+			const int r = c0 + PW + tid;
+			if (tid < LEAF - c0 - PW)
 			{
-				atomicCAS(info, 0, global_row0 + j + 1);
+				double x[PW], rdiag[PW];
+#pragma unroll
+				for (int k = 0; k < PW; k++)
+				{
+					x[k] = S[r * LP + c0 + k];
+					rdiag[k] = 1.0 / S[(c0 + k) * LP + c0 + k]; // independent divisions, off the substitution chain
+				}
+#pragma unroll
+				for (int j = 0; j < PW; j++)
+				{
+					double v = x[j];
+#pragma unroll
+					for (int k = 0; k < j; k++)
+					{
+						v = fma(-x[k], S[(c0 + j) * LP + c0 + k], v);
+					}
+					x[j] = v * rdiag[j];
+				}
+#pragma unroll
+				for (int k = 0; k < PW; k++)
+				{
+					S[r * LP + c0 + k] = x[k];
+				}
 			}
-			d = 1.0;
 		}
-		const double sd = sqrt(d);
-		if (q == 0)
+		__syncthreads();
+		// trailing update of the lower triangle: A22 -= P P^T, 8 x 8 tiles dealt round-robin to the warps
 		{
-			if (i > j)
+			const int t0 = c0 + PW;			  // first trailing row / column
+			const int m = (LEAF - t0) / 8;	  // tile rows
+			const int ntiles = m * (m + 1) / 2;
+			for (int idx = warp; idx < ntiles; idx += LEAF_THREADS / 32)
 			{
-				S[i * LP + j] = S[i * LP + j] / sd;
-			}
-			else if (i == j)
-			{
-				dg[j] = sd;
+				// idx -> (ti, tj), tj <= ti
+				int ti = int((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+				while ((ti + 1) * (ti + 2) / 2 <= idx)
+				{
+					ti++;
+				}
+				while (ti * (ti + 1) / 2 > idx)
+				{
+					ti--;
+				}
+				const int tj = idx - ti * (ti + 1) / 2;
+				const int r0 = t0 + ti * 8, q0 = t0 + tj * 8;
+				double2* cptr = reinterpret_cast<double2*>(S + (r0 + g) * LP + q0 + 2 * t);
+				const double2 cv = *cptr;
+				double c[2] = {-cv.x, -cv.y}; // accumulate -(A22) + P P^T, negate back on store
+#pragma unroll
+				for (int kk = 0; kk < PW / 4; kk++)
+				{
+					const double av = S[(r0 + g) * LP + c0 + kk * 4 + t];
+					const double bv = S[(q0 + g) * LP + c0 + kk * 4 + t];
+					gemm::dmma884(c, av, bv);
+				}
+				*cptr = make_double2(-c[0], -c[1]);
 			}
 		}
 		__syncthreads();
 	}
-	// inverse: column c of X = L^-1 by forward substitution, 4 lanes share one column
+
+	// ---------------------------------------------------------------- inverse
+	// diagonal 16 x 16 blocks: block i by lanes 0..15 of warp i; lane b owns column b of X_ii
+	if (lane < PW)
 	{
-		const int c = tid >> 2;
-		const int c0 = (tid >> 5) << 3; // first column of this warp
-		if (q == 0)
+		const int i0 = warp * PW, bcol = lane;
+		double x[PW];
+#pragma unroll
+		for (int a = 0; a < PW; a++)
 		{
-			S[c * LP + c + 1] = 1.0 / dg[c];
-		}
-		__syncwarp();
-		for (int r = c0 + 1; r < LEAF; r++)
-		{
-			double s = 0.0;
-			if (r > c)
+			double v = (a == bcol) ? 1.0 : 0.0;
+#pragma unroll
+			for (int k = 0; k < a; k++)
 			{
-				double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-				const double* lr = S + r * LP;
-				const double* xc = S + c * LP + 1;
-				int k = c + q;
-				for (; k + 12 < r; k += 16)
-				{
-					s = fma(lr[k], xc[k], s);
-					s1 = fma(lr[k + 4], xc[k + 4], s1);
-					s2 = fma(lr[k + 8], xc[k + 8], s2);
-					s3 = fma(lr[k + 12], xc[k + 12], s3);
-				}
-				for (; k < r; k += 4)
-				{
-					s = fma(lr[k], xc[k], s);
-				}
-				s = (s + s1) + (s2 + s3);
+				v = fma(-S[(i0 + a) * LP + i0 + k], (k >= bcol) ? x[k] : 0.0, v);
 			}
-			s += __shfl_xor_sync(0xffffffffu, s, 1);
-			s += __shfl_xor_sync(0xffffffffu, s, 2);
-			if (r > c && q == 0)
+			x[a] = (a >= bcol) ? v / S[(i0 + a) * LP + i0 + a] : 0.0;
+		}
+#pragma unroll
+		for (int a = 0; a < PW; a++)
+		{
+			if (a >= bcol)
 			{
-				S[c * LP + r + 1] = -s / dg[r];
+				S[(i0 + bcol) * LP + i0 + a + 1] = x[a]; // X[i0 + a][i0 + bcol], transposed + shifted
+			}
+		}
+	}
+	__syncthreads();
+	// block sub-diagonals d = 1 .. 7: block (i, j) = (j + d, j) by warp j
+	double* ws = scratch + warp * 16 * 20;
+	for (int d = 1; d < LEAF / PW; d++)
+	{
+		const int j = warp, i = j + d;
+		if (i < LEAF / PW)
+		{
+			// T = sum_{k = j}^{i - 1} L_ik X_kj   (16 x 16, as 2 x 2 DMMA tiles)
+			double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+			for (int k = j; k < i; k++)
+			{
+#pragma unroll
+				for (int kk = 0; kk < 4; kk++)
+				{
+					double av[2], bv[2];
+#pragma unroll
+					for (int mi = 0; mi < 2; mi++)
+					{
+						av[mi] = S[(i * PW + mi * 8 + g) * LP + k * PW + kk * 4 + t]; // L_ik[mi*8+g][kk*4+t]
+					}
+#pragma unroll
+					for (int nj = 0; nj < 2; nj++)
+					{
+						// X_kj[a][b], a = kk*4+t, b = nj*8+g, stored at S[j*16 + b][k*16 + a + 1]; X_jj is lower triangular
+						const int a = kk * 4 + t, b = nj * 8 + g;
+						const double v = S[(j * PW + b) * LP + k * PW + a + 1];
+						bv[nj] = (k > j || a >= b) ? v : 0.0;
+					}
+#pragma unroll
+					for (int mi = 0; mi < 2; mi++)
+					{
+#pragma unroll
+						for (int nj = 0; nj < 2; nj++)
+						{
+							gemm::dmma884(acc[mi][nj], av[mi], bv[nj]);
+						}
+					}
+				}
+			}
+			// T -> scratch (row-major 16 x 20) so that it can be re-read as a B operand
+#pragma unroll
+			for (int mi = 0; mi < 2; mi++)
+			{
+#pragma unroll
+				for (int nj = 0; nj < 2; nj++)
+				{
+					*reinterpret_cast<double2*>(ws + (mi * 8 + g) * 20 + nj * 8 + 2 * t) = make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+				}
 			}
 			__syncwarp();
+			// R = X_ii T ; X_ij = -R
+			double r[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+			for (int kk = 0; kk < 4; kk++)
+			{
+				double av[2], bv[2];
+#pragma unroll
+				for (int mi = 0; mi < 2; mi++)
+				{
+					// X_ii[a][b], a = mi*8+g, b = kk*4+t, stored at S[i*16 + b][i*16 + a + 1]; lower triangular
+					const int a = mi * 8 + g, b = kk * 4 + t;
+					const double v = S[(i * PW + b) * LP + i * PW + a + 1];
+					av[mi] = (a >= b) ? v : 0.0;
+				}
+#pragma unroll
+				for (int nj = 0; nj < 2; nj++)
+				{
+					bv[nj] = ws[(kk * 4 + t) * 20 + nj * 8 + g]; // T[kk*4+t][nj*8+g]
+				}
+#pragma unroll
+				for (int mi = 0; mi < 2; mi++)
+				{
+#pragma unroll
+					for (int nj = 0; nj < 2; nj++)
+					{
+						gemm::dmma884(r[mi][nj], av[mi], bv[nj]);
+					}
+				}
+			}
+			// X_ij[a][b] -> S[j*16 + b][i*16 + a + 1]
+#pragma unroll
+			for (int mi = 0; mi < 2; mi++)
+			{
+#pragma unroll
+				for (int nj = 0; nj < 2; nj++)
+				{
+#pragma unroll
+					for (int u = 0; u < 2; u++)
+					{
+						S[(j * PW + nj * 8 + 2 * t + u) * LP + i * PW + mi * 8 + g + 1] = -r[mi][nj][u];
+					}
+				}
+			}
 		}
+		__syncthreads();
 	}
-	__syncthreads();
 	for (int e = tid; e < LEAF * LEAF; e += LEAF_THREADS)
 	{
 		const int r = e >> 7, c = e & 127;
 		double l = 0.0, x = 0.0;
-		if (c < r)
+		if (c <= r)
 		{
 			l = S[r * LP + c];
-			x = S[c * LP + r + 1];
-		}
-		else if (c == r)
-		{
-			l = dg[r];
 			x = S[c * LP + r + 1];
 		}
 		A[size_t(r) * ld + c] = l;

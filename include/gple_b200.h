@@ -173,6 +173,9 @@ extern "C"
 	int gple_set_variance_gemm_variant(int variant);
 	/* Register-resident DMMA / DFMA loops: measured FP64 tensor and vector peaks of this GPU, in TFLOP/s. */
 	int gple_measure_fp64_peak(gple_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+	/* DMMA rate of the GEMM's own register tile (8 warps / SM, 32 accumulators, 8 + 4 changing operands, no memory):
+	 * the ceiling of a register-tiled mma.sync FP64 kernel at the occupancy of var_gemm_kernel. */
+	int gple_measure_dmma_tile_peak(gple_ctx* ctx, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,7 @@ NAMES = ["BK16 S4 2x4 (64x32)", "BK32 S3 2x4 (64x32)", "BK16 S4 4x4 (32x32)", "B
 ctx = L.Context(0)
 dmma, dfma = ctx.fp64_peak()
 print(f"measured peaks: DMMA {dmma:.2f} TFLOP/s, DFMA {dfma:.2f} TFLOP/s")
+print(f"register-tile DMMA ceiling (8 warps/SM, 8x4 tile, changing operands, no memory): {ctx.dmma_tile_peak():.2f} TFLOP/s")
 for n in (2048, 4096, 8192):
     rows = 148 * 128
     flops = rows * n * (n + 128.0)
