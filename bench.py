@@ -45,6 +45,7 @@ WORKLOAD = ("C2: Tully SAC, N=2048 training points/element, 3 elements (rho00,rh
             "step = TrainingKernels rebuild (3 elements) + evolve (8Q GPR predictions per element)")
 
 
+
 def make_inputs():
     sets = [syn.training_set(2, e, N_TRAIN, CENTRE) for e in range(3)]
     pts = []
@@ -279,6 +280,17 @@ def run_ours(args):
     ctx.profile_enable(False)
     clocks = sampler.stop()
 
+    rows_total = rows_var = rows_zero = 0
+    for c in train_ctx:
+        a_, b_, c_ = c.gate_statistics()
+        rows_total, rows_var, rows_zero = rows_total + a_, rows_var + b_, rows_zero + c_
+    # the same step with every variance computed (GPLE_OPT_GATED_VARIANCE = 0), for comparison
+    ctx.set_gated_variance(False)
+    reset()
+    resident()
+    full_ms = timed(resident, args.steps)
+    ctx.set_gated_variance(True)
+
     reset()
     host_step()  # warm the host path
     e2e_ms = timed(host_step, args.steps)
@@ -314,7 +326,11 @@ def run_ours(args):
                   "dmma_register_tile_ceiling_note": "same 8x4 DMMA register tile at 8 warps/SM with changing operands and no memory traffic: the ceiling of an mma.sync FP64 GEMM at this occupancy",
                   "kernel_build_gbs": kb_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else None, "kernel_build_share": kb_ms / total_ms,
                   "cholesky_inverse_tflops": fa_flops / (fa_ms * 1e-3) / 1e12 if fa_ms > 0 else None, "factorise_share": fa_ms / total_ms,
-                  "reference_formulation_tflops_equiv": alg_flops_step / (ms_per_step * 1e-3) / 1e12,
+                  "gated_variance": {"enabled": True, "rows_total": rows_total, "rows_through_variance_gemm": rows_var, "rows_decided_zero": rows_zero,
+                                     "fraction": rows_var / max(rows_total, 1),
+                                     "note": "cutoff gate == 1 exactly when |f|^2 >= 4 k** (computed variance never exceeds the prior k**), == 0 exactly when |f|^2 <= noise/2 (variance >= noise): those queries skip the variance GEMM; outputs agree to rounding (tests/test_gpu_dynamics.py)"},
+                  "value_with_every_variance_computed": 1000.0 / (full_ms / args.steps), "ms_per_step_with_every_variance_computed": full_ms / args.steps,
+                  "reference_formulation_tflops_equiv": alg_flops_step / ((full_ms / args.steps) * 1e-3) / 1e12,
                   "check": last_scalars},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -41,6 +41,8 @@ SIGNATURES = {
     "gple_ctx_destroy": (C.c_int, [_vp]),
     "gple_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "gple_ctx_sync": (C.c_int, [_vp]),
+    "gple_ctx_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "gple_gate_statistics": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
     "gple_last_error": (C.c_char_p, [_vp]),
     "gple_launch_count": (C.c_ulonglong, [_vp]),
     "gple_kernel_real": (C.c_int, [_vp, _dp, _sz, _dp, _sz, _dp, C.c_int, _dp, _dp]),
@@ -127,6 +129,14 @@ class Context:
 
     def set_stream(self, stream_ptr):
         self.check(self.lib.gple_ctx_set_stream(self.h, stream_ptr))
+
+    def set_gated_variance(self, on: bool):
+        self.check(self.lib.gple_ctx_set_option(self.h, 1, int(on)))
+
+    def gate_statistics(self):
+        out = (C.c_ulonglong * 3)()
+        self.check(self.lib.gple_gate_statistics(self.h, out))
+        return int(out[0]), int(out[1]), int(out[2])
 
     def sync(self):
         self.check(self.lib.gple_ctx_sync(self.h))

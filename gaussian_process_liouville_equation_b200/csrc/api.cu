@@ -198,7 +198,7 @@ extern "C"
 			{
 				GPLE_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
 				ctx->stream = ctx->own_stream;
-				ctx->h_pinned_count = 256;
+				ctx->h_pinned_count = 512;
 				GPLE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pinned), ctx->h_pinned_count * sizeof(double)));
 				cudaDeviceProp prop{};
 				GPLE_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -246,6 +246,29 @@ extern "C"
 			return GPLE_ERR_ARG;
 		}
 		ctx->stream = stream != nullptr ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
+		return GPLE_OK;
+	}
+
+	int gple_ctx_set_option(gple_ctx* ctx, int option, int value)
+	{
+		if (ctx == nullptr || option != GPLE_OPT_GATED_VARIANCE)
+		{
+			return GPLE_ERR_ARG;
+		}
+		ctx->gated_variance = value != 0;
+		return GPLE_OK;
+	}
+
+	int gple_gate_statistics(gple_ctx* ctx, unsigned long long out[3])
+	{
+		if (ctx == nullptr || out == nullptr)
+		{
+			return GPLE_ERR_ARG;
+		}
+		out[0] = ctx->gate_rows_total;
+		out[1] = ctx->gate_rows_variance;
+		out[2] = ctx->gate_rows_zero;
+		ctx->gate_rows_total = ctx->gate_rows_variance = ctx->gate_rows_zero = 0;
 		return GPLE_OK;
 	}
 
@@ -671,7 +694,7 @@ extern "C"
 			ctx,
 			[&]() -> int
 			{
-				require(slot >= 0 && slot < 3, "gple_profile_read: unknown slot");
+				require(slot >= 0 && slot < 4, "gple_profile_read: unknown slot");
 				sync(ctx);
 				auto& p = ctx->prof[slot];
 				double tot = 0.0;

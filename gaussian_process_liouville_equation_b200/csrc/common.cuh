@@ -133,6 +133,9 @@ struct gple_ctx
 	double* h_pinned = nullptr; // small pinned staging area for scalar read-backs
 	size_t h_pinned_count = 0;
 	int num_sms = 148;
+	// bound-gated variance (GPLE_OPT_GATED_VARIANCE) and its statistics
+	bool gated_variance = true;
+	unsigned long long gate_rows_total = 0, gate_rows_variance = 0, gate_rows_zero = 0;
 	// optional per-kernel event timing (gple_profile_*)
 	bool prof_on = false;
 	struct ProfSlot
@@ -140,7 +143,7 @@ struct gple_ctx
 		std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
 		double work = 0.0;
 		unsigned long long launches = 0;
-	} prof[3];
+	} prof[4];
 };
 
 namespace gple

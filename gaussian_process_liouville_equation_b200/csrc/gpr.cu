@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 	const long long Q,
 	const long long row0,
 	const int rows,
+	const int* __restrict__ row_list, // nullptr: composite row = row0 + r; else row_list[row0 + r] (r < list_count)
+	const long long list_count,
 	const double2* __restrict__ Xt,
 	const int N,
 	const int Np,
@@ -99,11 +101,17 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 	{
 		return;
 	}
-	const long long R = row0 + r;
+	long long R = row0 + r;
+	bool valid = true;
+	if (row_list != nullptr)
+	{
+		valid = R < list_count;
+		R = valid ? row_list[R] : 0;
+	}
 	const long long m = R / spec.nb;
 	const int rb = int(R - m * spec.nb);
 	double* __restrict__ out = A + size_t(r) * n;
-	if (m >= Q)
+	if (m >= Q || !valid)
 	{
 		for (int J = lane * 2; J < n; J += 64)
 		{
@@ -141,9 +149,152 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 	{
 		acc += __shfl_xor_sync(0xffffffffu, acc, o);
 	}
-	if (lane == 0)
+	if (lane == 0 && pred != nullptr)
 	{
 		pred[r] = acc;
+	}
+}
+
+/// Mean only: pred[R] = sum_j k(x_q, x_j) v_j for composite rows R = 0 .. total_rows-1 (kernel.cpp:495 /
+/// complex_kernel.cpp:608) without ever storing K*.  exp-bound: a tile of 256 training points (x, p, v) is staged in
+/// shared memory.  WARP_PER_ROW = false (large batches): one row per thread with 32 independent partial sums in
+/// registers, tile entries read as broadcasts, no shuffles; true (small batches): one warp per row.  Both walk the
+/// training points in exactly the order of kstar_kernel's fused mean (slot s takes columns 2s, 2s+1, 2s+64, ...; the
+/// slots are combined by the xor butterfly), so a prediction is bit-identical whichever kernel produced it.
+/// `coincident[R]` = 1 when the query equals a training point (the delta term of kernel.cpp:8-31 fired).
+template <bool WARP_PER_ROW>
+__global__ void __launch_bounds__(256) kmean_kernel(
+	const BlockSpec spec,
+	const double2* __restrict__ Xq,
+	const long long total_rows,
+	const double2* __restrict__ Xt,
+	const int N,
+	const int Np,
+	const double* __restrict__ w,
+	double* __restrict__ pred,
+	unsigned char* __restrict__ coincident
+)
+{
+	constexpr int TJ = 256, ROWS = WARP_PER_ROW ? 8 : 256;
+	__shared__ double4 tile[TJ];
+	const int lane = threadIdx.x & 31;
+	const long long R = (long long)blockIdx.x * ROWS + (WARP_PER_ROW ? threadIdx.x >> 5 : threadIdx.x);
+	const bool live = R < total_rows;
+	const long long m = live ? R / spec.nb : 0;
+	const int rb = int(live ? R - m * spec.nb : 0);
+	const double2 xq = Xq[m];
+	double acc[WARP_PER_ROW ? 1 : 32];
+#pragma unroll
+	for (int i = 0; i < (WARP_PER_ROW ? 1 : 32); i++)
+	{
+		acc[i] = 0.0;
+	}
+	bool hit = false;
+	for (int cb = 0; cb < spec.nb; cb++)
+	{
+		const GaussBlock g = spec.b[rb][cb];
+		for (int j0 = 0; j0 < Np; j0 += TJ)
+		{
+			__syncthreads();
+			{
+				const int j = j0 + threadIdx.x;
+				const double2 x = j < N ? Xt[j] : make_double2(0.0, 0.0);
+				tile[threadIdx.x] = make_double4(x.x, x.y, j < N ? w[cb * Np + j] : 0.0, 0.0);
+			}
+			__syncthreads();
+			if (WARP_PER_ROW)
+			{
+#pragma unroll
+				for (int k = 0; k < TJ / 64; k++)
+				{
+#pragma unroll
+					for (int u = 0; u < 2; u++)
+					{
+						const int j = 64 * k + 2 * lane + u;
+						if (j0 + j < N)
+						{
+							const double4 t = tile[j];
+							const bool same = xq.x == t.x && xq.y == t.y;
+							hit |= same;
+							const double val = gauss_value(g, xq, make_double2(t.x, t.y)) + (same ? g.diag_add : 0.0);
+							acc[0] += val * t.z;
+						}
+					}
+				}
+			}
+			else
+			{
+				for (int k = 0; k < TJ / 64; k++)
+				{
+					if (j0 + 64 * k >= N)
+					{
+						break;
+					}
+#pragma unroll
+					for (int sl = 0; sl < 32; sl++)
+					{
+#pragma unroll
+						for (int u = 0; u < 2; u++)
+						{
+							const int j = 64 * k + 2 * sl + u;
+							if (j0 + j < N)
+							{
+								const double4 t = tile[j];
+								const bool same = xq.x == t.x && xq.y == t.y;
+								hit |= same;
+								const double val = gauss_value(g, xq, make_double2(t.x, t.y)) + (same ? g.diag_add : 0.0);
+								acc[sl] += val * t.z;
+							}
+						}
+					}
+				}
+			}
+		}
+	}
+	double total;
+	if (WARP_PER_ROW)
+	{
+		total = acc[0];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			total += __shfl_xor_sync(0xffffffffu, total, o);
+			hit |= __shfl_xor_sync(0xffffffffu, int(hit), o) != 0;
+		}
+	}
+	else
+	{
+		// the xor butterfly as seen by lane 0: a[i] += a[i ^ o] for o = 16, 8, 4, 2, 1
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+#pragma unroll
+			for (int i = 0; i < o; i++)
+			{
+				acc[i] += acc[i + o];
+			}
+		}
+		total = acc[0];
+	}
+	if (live && (!WARP_PER_ROW || lane == 0))
+	{
+		pred[R] = total;
+		if (coincident != nullptr)
+		{
+			coincident[R] = hit ? 1 : 0;
+		}
+	}
+}
+
+void launch_kmean(gple_ctx* ctx, const BlockSpec& spec, const double2* Xq, long long total_rows, const double2* Xt, int N, int Np, const double* w, double* pred, unsigned char* coincident)
+{
+	if (total_rows >= 148ll * 256)
+	{
+		GPLE_LAUNCH(ctx, kmean_kernel<false>, unsigned((total_rows + 255) / 256), 256, 0, spec, Xq, total_rows, Xt, N, Np, w, pred, coincident);
+	}
+	else
+	{
+		GPLE_LAUNCH(ctx, kmean_kernel<true>, unsigned((total_rows + 7) / 8), 256, 0, spec, Xq, total_rows, Xt, N, Np, w, pred, coincident);
 	}
 }
 
@@ -330,6 +481,60 @@ void launch_var_gemm(gple_ctx* ctx, int variant, const double* A, const double* 
 	}
 }
 
+/// Bound-gated variance.  The cutoff gate of kernel.h:301-332 is decided without the variance for two sets of queries:
+///  * |f|^2 >= 4 k**: the computed variance k** - sum Z^2 can never exceed the prior k**, so the gate is exactly 1;
+///  * |f|^2 <= noise/2 where noise = sigma_f^2 sigma_n^2 (complex: sigma^2 sigma_n^2) and the query coincides with no
+///    training point: k K^-1 k^T <= the latent prior variance (Schur complement of the noise-free covariance, for the
+///    complex element of the composite [Re; Im] process), so var >= noise > |f|^2 and the gate is exactly 0.  Used only
+///    when noise >= 1e-9 k**, far above the rounding error of the computed variance.
+/// Collects the rows of the remaining queries (both rows of a complex query) into `idx` and records each row's slot
+/// (-1: gate 1, -2: gate 0).  counter[0] = rows collected, counter[1] = rows decided 0.
+__global__ void __launch_bounds__(256) classify_kernel(const double* __restrict__ pred, const unsigned char* __restrict__ coincident, const int points, const int nb, const double four_prior, const double half_noise, int* __restrict__ idx, int* __restrict__ slot, int* __restrict__ counter)
+{
+	const int p = blockIdx.x * 256 + threadIdx.x;
+	bool need = false, zero = false;
+	if (p < points)
+	{
+		double f2 = 0.0;
+		bool hit = false;
+		for (int k = 0; k < nb; k++)
+		{
+			const double f = pred[p * nb + k];
+			f2 = fma(f, f, f2);
+			hit |= coincident[p * nb + k] != 0;
+		}
+		zero = !hit && f2 <= half_noise;	   // half_noise < 0 disables the lower bound
+		need = !(f2 >= four_prior) && !zero; // NaN keeps the full path
+	}
+	const unsigned ballot = __ballot_sync(0xffffffffu, need), zballot = __ballot_sync(0xffffffffu, zero);
+	const int lane = threadIdx.x & 31;
+	int base = 0;
+	if (lane == 0)
+	{
+		if (ballot != 0u)
+		{
+			base = atomicAdd(counter, __popc(ballot) * nb);
+		}
+		if (zballot != 0u)
+		{
+			atomicAdd(counter + 1, __popc(zballot) * nb);
+		}
+	}
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (p < points)
+	{
+		const int mine = base + __popc(ballot & ((1u << lane) - 1u)) * nb;
+		for (int k = 0; k < nb; k++)
+		{
+			slot[p * nb + k] = need ? mine + k : (zero ? -2 : -1);
+			if (need)
+			{
+				idx[mine + k] = p * nb + k;
+			}
+		}
+	}
+}
+
 /// kernel.cpp:496-519 + kernel.h:301-332: variance, cubic gate, cutoff prediction (real element)
 __device__ __forceinline__ double gate_factor(const double pred_sq, const double abs_pred, const double var)
 {
@@ -345,15 +550,17 @@ __device__ __forceinline__ double gate_factor(const double pred_sq, const double
 	return (5.0 - 2.0 * a) * (a - 1.0) * (a - 1.0);
 }
 
-__global__ void finalize_real_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double* __restrict__ pred_out, double* __restrict__ var_out, double* __restrict__ cut_out)
+__global__ void finalize_real_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double* __restrict__ pred_out, double* __restrict__ var_out, double* __restrict__ cut_out)
 {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= rows || row0 + r >= Q)
 	{
 		return;
 	}
-	const double f = pred[r], var = prior - q[r];
-	const double gate = gate_factor(f * f, fabs(f), var);
+	const double f = pred[r];
+	const int sl = slot != nullptr ? slot[r] : r;
+	const double var = sl >= 0 ? prior - q[sl] : prior; // sl < 0: gate decided by a bound (classify_kernel), variance not computed
+	const double gate = sl >= 0 ? gate_factor(f * f, fabs(f), var) : (sl == -1 ? 1.0 : 0.0);
 	if (pred_out != nullptr)
 	{
 		pred_out[row0 + r] = f;
@@ -369,7 +576,7 @@ __global__ void finalize_real_kernel(const double* __restrict__ pred, const doub
 }
 
 /// complex_kernel.cpp:608-643 in composite form: rows (2m, 2m+1) = (Re, Im) parts of query m
-__global__ void finalize_complex_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double2* __restrict__ pred_out, double* __restrict__ var_out, double2* __restrict__ cut_out)
+__global__ void finalize_complex_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double2* __restrict__ pred_out, double* __restrict__ var_out, double2* __restrict__ cut_out)
 {
 	const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
 	const long long m = row0 / 2 + pidx;
@@ -378,9 +585,10 @@ __global__ void finalize_complex_kernel(const double* __restrict__ pred, const d
 		return;
 	}
 	const double fr = pred[2 * pidx], fi = pred[2 * pidx + 1];
-	const double var = prior - q[2 * pidx] - q[2 * pidx + 1];
+	const int sl = slot != nullptr ? slot[2 * pidx] : 2 * pidx;
+	const double var = sl >= 0 ? prior - q[sl] - q[sl + 1] : prior;
 	const double ps = fr * fr + fi * fi;
-	const double gate = gate_factor(ps, hypot(fr, fi), var);
+	const double gate = sl >= 0 ? gate_factor(ps, hypot(fr, fi), var) : (sl == -1 ? 1.0 : 0.0);
 	if (pred_out != nullptr)
 	{
 		pred_out[m] = make_double2(fr, fi);
@@ -849,6 +1057,14 @@ double quadform(gple_ctx* ctx, const gple_model* m, const QuadSpec& qs, const do
 
 constexpr int CHUNK_ROWS = 148 * 128;
 
+void require_rows(long long total_rows)
+{
+	if (total_rows >= (1ll << 31) - 256)
+	{
+		throw ArgError{"gated prediction: more than 2^31 composite rows in one call"};
+	}
+}
+
 } // namespace
 
 void gpr_setup_attributes()
@@ -1037,6 +1253,13 @@ int train_complex(gple_ctx* ctx, const double* X_, const double* y_, size_t N, c
 }
 
 /// Batched prediction of `Q` points on the device.  d_pred / d_cut hold nb doubles per point.
+///
+/// Two schedules:
+///  * every variance (var_out requested, or GPLE_OPT_GATED_VARIANCE off): chunks of 18944 composite rows, per chunk
+///    K* rows + fused mean -> triangular variance GEMM -> gate;
+///  * bound-gated (only the cutoff prediction is wanted): one mean-only pass over all queries (K* never stored),
+///    classification by |f|^2 >= 4 k**, then K* rows + variance GEMM in FULL chunks over the compacted list of the
+///    remaining queries, so the GEMM always runs at full occupancy.
 void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size_t Q, const double* d_yq, double* d_pred, double* d_var, double* d_cut, double* d_err)
 {
 	gpr_setup_attributes();
@@ -1046,36 +1269,97 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 	const int n = m->n;
 	const int max_rows = int(std::min<long long>(CHUNK_ROWS, (long long)round_up(size_t(total_rows), 128)));
 	double* A = ctx->ws.get<double>("pred.A", size_t(max_rows) * n);
-	double* pred = ctx->ws.get<double>("pred.f", size_t(max_rows));
-	double* q = ctx->ws.get<double>("pred.q", size_t(max_rows) * MAX_VAR_SPLITS);
+	const double2* Xq2 = reinterpret_cast<const double2*>(d_Xq);
+	const double2* Xt2 = reinterpret_cast<const double2*>(m->X);
 	if (d_err != nullptr)
 	{
 		GPLE_CUDA(cudaMemsetAsync(d_err, 0, sizeof(double), ctx->stream));
 	}
+	const bool want_gate = d_var != nullptr || d_cut != nullptr;
+	if (d_var == nullptr && d_cut != nullptr && ctx->gated_variance)
+	{
+		const size_t rows_pad = round_up(size_t(total_rows), 128);
+		double* pred = ctx->ws.get<double>("pred.f_all", rows_pad);
+		unsigned char* coincident = ctx->ws.get<unsigned char>("pred.coincident", rows_pad);
+		int* gate_idx = ctx->ws.get<int>("pred.gate_idx", rows_pad);
+		int* gate_slot = ctx->ws.get<int>("pred.gate_slot", rows_pad);
+		int* gate_cnt = ctx->ws.get<int>("pred.gate_cnt", 4);
+		require_rows(total_rows);
+		{
+			ProfScope prof(ctx, GPLE_PROF_MEAN, double(total_rows) * double(m->N) * nb, 1);
+			launch_kmean(ctx, spec, Xq2, total_rows, Xt2, int(m->N), m->Np, m->v, pred, coincident);
+		}
+		const double noise = m->theta[0] * m->theta[0] * m->theta[m->is_complex ? 7 : 3] * m->theta[m->is_complex ? 7 : 3];
+		const double half_noise = noise >= 1e-9 * m->prior ? 0.5 * noise : -1.0;
+		GPLE_CUDA(cudaMemsetAsync(gate_cnt, 0, 4 * sizeof(int), ctx->stream));
+		GPLE_LAUNCH(ctx, classify_kernel, unsigned((Q + 255) / 256), 256, 0, pred, coincident, int(Q), nb, 4.0 * m->prior, half_noise, gate_idx, gate_slot, gate_cnt);
+		GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 200, gate_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
+		int counts[2] = {0, 0};
+		std::memcpy(counts, ctx->h_pinned + 200, sizeof(counts));
+		const int count = counts[0];
+		ctx->gate_rows_total += (unsigned long long)total_rows;
+		ctx->gate_rows_variance += (unsigned long long)count;
+		ctx->gate_rows_zero += (unsigned long long)counts[1];
+		double* q = ctx->ws.get<double>("pred.q_all", round_up(size_t(count), 128) + size_t(CHUNK_ROWS) * MAX_VAR_SPLITS);
+		for (long long c0 = 0; c0 < count; c0 += CHUNK_ROWS)
+		{
+			const int rows_real = int(std::min<long long>(CHUNK_ROWS, count - c0));
+			const int rows = int(round_up(size_t(rows_real), 128));
+			{
+				ProfScope prof(ctx, GPLE_PROF_KERNEL_BUILD, 8.0 * double(rows) * n, 1);
+				GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, c0, rows, gate_idx, (long long)count, Xt2, int(m->N), m->Np, n, m->v, A, nullptr);
+			}
+			ProfScope prof(ctx, GPLE_PROF_VARIANCE_GEMM, double(rows) * n * (double(n) + 128.0), 1);
+			launch_var_gemm(ctx, g_var_variant, A, m->W, n, rows, q + c0);
+		}
+		if (m->is_complex)
+		{
+			GPLE_LAUNCH(ctx, finalize_complex_kernel, unsigned((total_rows / 2 + 255) / 256), 256, 0, pred, q, gate_slot, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
+		}
+		else
+		{
+			GPLE_LAUNCH(ctx, finalize_real_kernel, unsigned((total_rows + 255) / 256), 256, 0, pred, q, gate_slot, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
+		}
+		if (d_err != nullptr && d_yq != nullptr)
+		{
+			for (long long row0 = 0; row0 < total_rows; row0 += CHUNK_ROWS)
+			{
+				const int rows = int(std::min<long long>(CHUNK_ROWS, total_rows - row0));
+				GPLE_LAUNCH(ctx, sqerr_kernel, 1, 1024, 0, pred + row0, rows, row0, total_rows, d_yq, nb, nb, m->rescale, d_err);
+			}
+		}
+		return;
+	}
+	double* pred = ctx->ws.get<double>("pred.f", size_t(max_rows));
+	double* q = ctx->ws.get<double>("pred.q", size_t(max_rows) * MAX_VAR_SPLITS);
 	for (long long row0 = 0; row0 < total_rows; row0 += CHUNK_ROWS)
 	{
 		const int rows_real = int(std::min<long long>(CHUNK_ROWS, total_rows - row0));
 		const int rows = int(round_up(size_t(rows_real), 128));
+		if (want_gate)
 		{
-			ProfScope prof(ctx, GPLE_PROF_KERNEL_BUILD, 8.0 * double(rows) * n, 1);
-		GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, reinterpret_cast<const double2*>(d_Xq), (long long)Q, row0, rows, reinterpret_cast<const double2*>(m->X), int(m->N), m->Np, n, m->v, A, pred);
-		}
-		if (d_var != nullptr || d_cut != nullptr)
-		{
+			{
+				ProfScope prof(ctx, GPLE_PROF_KERNEL_BUILD, 8.0 * double(rows) * n, 1);
+				GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, row0, rows, nullptr, 0ll, Xt2, int(m->N), m->Np, n, m->v, A, pred);
+			}
 			ProfScope prof(ctx, GPLE_PROF_VARIANCE_GEMM, double(rows) * n * (double(n) + 128.0), 1);
 			launch_var_gemm(ctx, g_var_variant, A, m->W, n, rows, q);
 		}
 		else
 		{
+			// mean only (e.g. the loss evaluation of opt.cpp:441-482 without gradient): K* is never stored
+			ProfScope prof(ctx, GPLE_PROF_MEAN, double(rows_real) * double(m->N) * nb, 1);
+			launch_kmean(ctx, spec, Xq2 + row0 / nb, rows_real, Xt2, int(m->N), m->Np, m->v, pred, nullptr);
 			GPLE_CUDA(cudaMemsetAsync(q, 0, size_t(rows) * sizeof(double), ctx->stream));
 		}
 		if (m->is_complex)
 		{
-			GPLE_LAUNCH(ctx, finalize_complex_kernel, (rows / 2 + 255) / 256, 256, 0, pred, q, rows, row0, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
+			GPLE_LAUNCH(ctx, finalize_complex_kernel, (rows / 2 + 255) / 256, 256, 0, pred, q, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
 		}
 		else
 		{
-			GPLE_LAUNCH(ctx, finalize_real_kernel, (rows + 255) / 256, 256, 0, pred, q, rows, row0, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
+			GPLE_LAUNCH(ctx, finalize_real_kernel, (rows + 255) / 256, 256, 0, pred, q, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
 		}
 		if (d_err != nullptr && d_yq != nullptr)
 		{

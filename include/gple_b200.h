@@ -63,6 +63,22 @@ extern "C"
 	/* Number of CUDA kernels this context has launched since creation (bench.py's `gpu_launches`). */
 	unsigned long long gple_launch_count(const gple_ctx* ctx);
 	const char* gple_version(void);
+	/* Options.  GPLE_OPT_GATED_VARIANCE (default 1): when a caller only asks for the CUTOFF prediction (gple_evolve,
+	 * gple_new_point_predict, gple_predict_* with var_out == NULL), the variance GEMM is run only for the queries whose
+	 * gate (gple/kernel.h:301-332) is not already decided by a bound on the variance:
+	 *   |f|^2 >= 4 k**                  => gate == 1  (the computed variance k** - sum Z^2 never exceeds the prior k**);
+	 *   |f|^2 <= sigma_f^2 sigma_n^2 / 2 => gate == 0  (var >= sigma_f^2 sigma_n^2 for a query that coincides with no
+	 *                                                   training point; only used while the noise is >= 1e-9 k**).
+	 * The decided queries get exactly the value the full computation gives; the others go through the variance GEMM in a
+	 * different batch composition (summation order inside the GEMM may differ).  Set 0 to force every variance. */
+	enum gple_option
+	{
+		GPLE_OPT_GATED_VARIANCE = 1
+	};
+	int gple_ctx_set_option(gple_ctx* ctx, int option, int value);
+	/* Gated predictions since the last call (then reset): out = {composite rows seen, rows sent through the variance
+	 * GEMM, rows decided gate == 0}; the rest were decided gate == 1. */
+	int gple_gate_statistics(gple_ctx* ctx, unsigned long long out[3]);
 
 	/* ---- kernel matrices ---------------------------------------------------------------------------
 	 * Replaces KernelBase::KernelBase + delta_kernel (gple/kernel.cpp:8-31,217-242) and calculate_derivative
@@ -163,7 +179,8 @@ extern "C"
 	{
 		GPLE_PROF_VARIANCE_GEMM = 0, /* var_gemm_kernel: Z = K* W^T with fused row sum of squares; flops */
 		GPLE_PROF_KERNEL_BUILD = 1,	 /* kstar_kernel: K* rows + fused mean; bytes written */
-		GPLE_PROF_FACTORISE = 2		 /* potrf + trtri (all their launches together); flops = 2 n^3 / 3 */
+		GPLE_PROF_FACTORISE = 2,	 /* potrf + trtri (all their launches together); flops = 2 n^3 / 3 */
+		GPLE_PROF_MEAN = 3			 /* kmean_kernel: mean K* v without storing K*; work = exp evaluations */
 	};
 	int gple_profile_enable(gple_ctx* ctx, int on);
 	int gple_profile_read(gple_ctx* ctx, int slot, double* total_ms, unsigned long long* launches, double* work);

@@ -83,3 +83,29 @@ def test_observables_parity(dyn, oracle):
     a, b = dyn.observable_sums(1, pts, syn.MASS, 1), oracle.observable_sums(1, pts, syn.MASS, 1)
     assert np.abs(a - b).max() <= 1e-11 * np.abs(b).max()
     assert dyn.calculate_total_energy_average_one_surface(1, pts, syn.MASS, 1) == pytest.approx(b[7] / b[0], rel=1e-11)
+
+
+def test_bound_gated_variance_changes_nothing(dyn):
+    """GPLE_OPT_GATED_VARIANCE only skips variances whose gate is decided by var <= k**: coordinates are bit-identical
+    and densities agree to rounding with the option on and off (the rows that still go through the variance GEMM may
+    use a different n-split, i.e. a different summation order of the same terms); rows must have been skipped."""
+    from gaussian_process_liouville_equation_b200 import _lib as L
+
+    ctx = L.default_context()
+    n, centre = 300, (-0.8, syn.P0)
+    sets, g = build_models(n, centre, True)
+    pts = []
+    for e in range(3):
+        Xe, ye = syn.extra_points(21, e, sets[e][0], 5000, centre)
+        pts.append(syn.points_aos(Xe, ye))
+    ctx.gate_statistics()
+    ctx.set_gated_variance(True)
+    a = dyn.evolve(1, pts, syn.MASS, 1.0, g)
+    total, needed, zero = ctx.gate_statistics()
+    ctx.set_gated_variance(False)
+    b = dyn.evolve(1, pts, syn.MASS, 1.0, g)
+    ctx.set_gated_variance(True)
+    for e in range(3):
+        assert np.array_equal(a[e][:, :2], b[e][:, :2])
+        assert np.abs(a[e][:, 2:] - b[e][:, 2:]).max() <= 1e-12 * np.abs(b[e][:, 2:]).max()
+    assert total == (8 + 8 + 16) * 5000 and 0 < needed < 0.9 * total and 0 <= zero < total - needed
