@@ -50,6 +50,7 @@ SIGNATURES = {
     "gple_train_real": (C.c_int, [_vp, _dp, _dp, _sz, _dp, C.c_uint, C.POINTER(_vp), C.POINTER(RealScalars)]),
     "gple_train_complex": (C.c_int, [_vp, _dp, _dp, _sz, _dp, C.c_uint, C.POINTER(_vp), C.POINTER(ComplexScalars)]),
     "gple_model_get": (C.c_int, [_vp, _vp, C.c_int, _dp]),
+    "gple_model_nlml": (C.c_int, [_vp, _vp, _dp, _dp]),
     "gple_model_is_complex": (C.c_int, [_vp]),
     "gple_model_size": (_sz, [_vp]),
     "gple_model_destroy": (C.c_int, [_vp, _vp]),

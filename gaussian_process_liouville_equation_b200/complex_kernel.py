@@ -48,6 +48,13 @@ class TrainingComplexKernel:
     def get_magnitude(self):
         return self._s.magnitude
 
+    def get_negative_log_marginal_likelihood(self, grad: bool = False):
+        """NLML / LLT objective of test/gpr.cpp:470-532 on this model (value, or (value, gradient[8]))."""
+        v = C.c_double()
+        g = np.empty(8) if grad else None
+        self.ctx.check(self.ctx.lib.gple_model_nlml(self.ctx.h, self.h, C.byref(v), L.addr(g) if grad else None))
+        return (v.value, g) if grad else v.value
+
     def get_error(self):
         assert self._flags & L.CALC_ERROR
         return self._s.error

@@ -358,6 +358,18 @@ extern "C"
 	{
 		return m != nullptr ? m->is_complex : -1;
 	}
+	int gple_model_nlml(gple_ctx* ctx, gple_model* m, double* value, double* grad)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(m != nullptr && value != nullptr, "gple_model_nlml: null argument");
+				nlml_device(ctx, m, value, grad);
+				return GPLE_OK;
+			}
+		);
+	}
 	size_t gple_model_size(const gple_model* m)
 	{
 		return m != nullptr ? m->N : 0;

@@ -21,4 +21,6 @@ void real_derivatives(gple_ctx* ctx, gple_model* m, unsigned flags, const double
 void complex_derivatives(gple_ctx* ctx, gple_model* m, unsigned flags, const double* h_scal, gple_complex_scalars* r);
 /// d(validation error)/d theta for a model trained with GPLE_CALC_DERIVATIVE; d_cut / d_yq as in predict_device
 void validation_gradient(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size_t Q, const double* d_yq, const double* d_cut, double* h_grad);
+/// NLML / LLT objective (test/gpr.cpp:470-532) of a trained model; grad (nparam doubles, host) may be null
+void nlml_device(gple_ctx* ctx, gple_model* m, double* value, double* grad);
 } // namespace gple

@@ -595,6 +595,89 @@ __global__ void sum8_kernel(const double* __restrict__ part, const int blocks, d
 	}
 }
 
+/// NLML scalars (test/gpr.cpp:515): out[0] = sum_I ln L_II = -sum ln W_II (padding rows have W_II = 1),
+/// out[1] = y'^T v, out[2] = v^T v, out[3] = tr(M) over the real rows (M = full inverse, may be null).
+__global__ void __launch_bounds__(1024) nlml_scalars_kernel(const double* __restrict__ W, const double* __restrict__ M, const double* __restrict__ label, const double* __restrict__ v, const int N, const int Np, const int n, double* __restrict__ out)
+{
+	__shared__ double scratch[4 * 32];
+	double s[4] = {0.0, 0.0, 0.0, 0.0};
+	for (int I = threadIdx.x; I < n; I += 1024)
+	{
+		const bool real_row = I % Np < N;
+		s[0] -= log(W[size_t(I) * n + I]);
+		s[1] = fma(label[I], v[I], s[1]);
+		s[2] = fma(v[I], v[I], s[2]);
+		s[3] += (real_row && M != nullptr) ? M[size_t(I) * n + I] : 0.0;
+	}
+	block_reduce<4, 1024>(s, scratch);
+	if (threadIdx.x == 0)
+	{
+		out[0] = s[0];
+		out[1] = s[1];
+		out[2] = s[2];
+		out[3] = s[3];
+	}
+}
+
+/// tr[(M - w w^T) D] = sum_IJ (M_IJ - w_I w_J) D(I, J) for a composite matrix D generated on the fly (never stored):
+/// the gradient of the NLML (test/gpr.cpp:487-493, :523).  One CTA per 128 x 128 tile; partials summed by sum_kernel-like pass.
+__global__ void __launch_bounds__(256) trace_quad_kernel(const CompTerms ct, const double2* __restrict__ X, const int N, const int Np, const int n, const double* __restrict__ M, const double* __restrict__ w, double* __restrict__ part)
+{
+	__shared__ double2 xr[128], xc[128];
+	__shared__ double wr[128], wc[128];
+	__shared__ double scratch[8];
+	const int I0 = blockIdx.y * 128, J0 = blockIdx.x * 128;
+	const int rb = I0 / Np, cb = J0 / Np;
+	const int i0 = I0 - rb * Np, j0 = J0 - cb * Np;
+	if (threadIdx.x < 128)
+	{
+		xr[threadIdx.x] = X[i0 + threadIdx.x];
+		wr[threadIdx.x] = w[I0 + threadIdx.x];
+	}
+	else
+	{
+		xc[threadIdx.x - 128] = X[j0 + threadIdx.x - 128];
+		wc[threadIdx.x - 128] = w[J0 + threadIdx.x - 128];
+	}
+	__syncthreads();
+	const BlockTerms& bt = ct.b[rb + cb];
+	double s[1] = {0.0};
+	if (bt.n > 0)
+	{
+		const int c = threadIdx.x & 127;
+		if (j0 + c < N)
+		{
+			for (int r = threadIdx.x >> 7; r < 128 && i0 + r < N; r += 2)
+			{
+				const double a = M[size_t(I0 + r) * n + J0 + c] - wr[r] * wc[c];
+				s[0] = fma(a, eval_terms(bt, xr[r], xc[c]), s[0]);
+			}
+		}
+	}
+	block_reduce<1, 256>(s, scratch);
+	if (threadIdx.x == 0)
+	{
+		part[blockIdx.y * gridDim.x + blockIdx.x] = s[0];
+	}
+}
+
+/// out[k] = sum of part[k][0 .. count)
+__global__ void __launch_bounds__(1024) sum_rows_kernel(const double* __restrict__ part, const int count, double* __restrict__ out)
+{
+	__shared__ double scratch[32];
+	double s[1] = {0.0};
+	const double* p = part + size_t(blockIdx.x) * count;
+	for (int i = threadIdx.x; i < count; i += 1024)
+	{
+		s[0] += p[i];
+	}
+	block_reduce<1, 1024>(s, scratch);
+	if (threadIdx.x == 0)
+	{
+		out[blockIdx.x] = s[0];
+	}
+}
+
 void read_back(gple_ctx* ctx, const double* d, int count, double* h)
 {
 	GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned, d, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -720,6 +803,30 @@ void push(BlockTerms& b, const Term& t)
 		b.t[b.n++] = t;
 	}
 }
+/// Composite derivative of the covariance blocks over sub-kernel parameter p = 1..6 (sigma_R, l_Rx, l_Rp, sigma_I, l_Ix,
+/// l_Ip), including the chain rule through the derived correlation kernel (complex_kernel.cpp:37-46, 96-126), times
+/// `scale` (1: the reference's arrays, which lack sigma^2 -- quirk q2; sigma^2: the true derivative of C).
+CompTerms sub_param_terms(const CSub& c, const int p, const double scale)
+{
+	const bool isR = p <= 3;
+	const int d = isR ? p - 2 : p - 5; // -1: sub-magnitude
+	const double smag = isR ? c.sr : c.si;
+	const double* sl = isR ? c.lr : c.li;
+	CompTerms ct{};
+	BlockTerms& diag = ct.b[isR ? 0 : 2];
+	if (d < 0)
+	{
+		push(diag, term(smag, sl, scale * 2.0 / smag, 0));
+		push(ct.b[1], term(c.sc, c.lc, scale / smag, 0));
+	}
+	else
+	{
+		push(diag, term(smag, sl, scale, 1 + d));
+		push(ct.b[1], term(c.sc, c.lc, scale * (1.0 / sl[d] - sl[d] / (c.lc[d] * c.lc[d])), 0));
+		push(ct.b[1], term(c.sc, c.lc, scale * 0.5 * sl[d] / c.lc[d], 1 + d));
+	}
+	return ct;
+}
 /// purity auxiliary kernels (kernel.h:285-294, complex_kernel.cpp:206-219): magnitude and lengths
 struct Aux
 {
@@ -779,23 +886,7 @@ void complex_derivatives(gple_ctx* ctx, gple_model* m, unsigned flags, const dou
 	// p = 1..6: sub-kernel parameters (complex_kernel.cpp:37-46, 96-126), blocks WITHOUT sigma^2 (quirk q2)
 	for (int p = 1; p <= 6; p++)
 	{
-		const bool isR = p <= 3;
-		const int d = isR ? p - 2 : p - 5; // -1: sub-magnitude
-		const double smag = isR ? c.sr : c.si;
-		const double* sl = isR ? c.lr : c.li;
-		CompTerms ct{};
-		BlockTerms& diag = ct.b[isR ? 0 : 2];
-		if (d < 0)
-		{
-			push(diag, term(smag, sl, 2.0 / smag, 0));
-			push(ct.b[1], term(c.sc, c.lc, 1.0 / smag, 0));
-		}
-		else
-		{
-			push(diag, term(smag, sl, 1.0, 1 + d));
-			push(ct.b[1], term(c.sc, c.lc, 1.0 / sl[d] - sl[d] / (c.lc[d] * c.lc[d]), 0));
-			push(ct.b[1], term(c.sc, c.lc, 0.5 * sl[d] / c.lc[d], 1 + d));
-		}
+		const CompTerms ct = sub_param_terms(c, p, 1.0);
 		GPLE_LAUNCH(ctx, build_comp_kernel, dim3(n / 128, n / 128), 256, 0, ct, X, N, Np, n, Dm);
 		gemm::GemmArgs a{};
 		a.A = m->Kinv;
@@ -955,4 +1046,62 @@ void validation_gradient(gple_ctx* ctx, const gple_model* m, const double* d_Xq,
 	h_grad[3] = 2.0 * (0.0 + h[5]);
 }
 
+/// NLML / LLT objective of test/gpr.cpp:470-532 on a trained element model:
+///   value = y'^T v / 2 + sum ln L_II,   grad_p = tr[(M - v v^T) dC/dtheta_p] / 2   (M = C^-1, true derivatives).
+/// The magnitude and noise components are closed forms (tr(M C) = rows, dC/dsigma_n proportional to I); the length and
+/// sub-kernel components generate dC on the fly.  Complex element: composite [Re f; Im f] process.
+void nlml_device(gple_ctx* ctx, gple_model* m, double* value, double* grad)
+{
+	const int N = int(m->N), Np = m->Np, n = m->n;
+	const double2* X = reinterpret_cast<const double2*>(m->X);
+	double* out = ctx->ws.get<double>("nlml.out", 16);
+	if (grad != nullptr)
+	{
+		ensure_full_inverse(ctx, m);
+	}
+	GPLE_LAUNCH(ctx, nlml_scalars_kernel, 1, 1024, 0, m->W, grad != nullptr ? m->Kinv : nullptr, m->label, m->v, N, Np, n, out);
+	const int np = m->nparam();
+	const int tiles = (n / 128) * (n / 128);
+	int generated[6], ng = 0;
+	if (grad != nullptr)
+	{
+		double* part = ctx->ws.get<double>("nlml.part", size_t(6) * tiles);
+		if (m->is_complex)
+		{
+			const CSub c = csub(m->theta);
+			for (int p = 1; p <= 6; p++)
+			{
+				const CompTerms ct = sub_param_terms(c, p, m->theta[0] * m->theta[0]);
+				GPLE_LAUNCH(ctx, trace_quad_kernel, dim3(n / 128, n / 128), 256, 0, ct, X, N, Np, n, m->Kinv, m->v, part + size_t(ng) * tiles);
+				generated[ng++] = p;
+			}
+		}
+		else
+		{
+			const double l[2] = {m->theta[1], m->theta[2]};
+			for (int d = 0; d < 2; d++)
+			{
+				CompTerms ct{};
+				push(ct.b[0], term(m->theta[0], l, 1.0, 1 + d));
+				GPLE_LAUNCH(ctx, trace_quad_kernel, dim3(n / 128, n / 128), 256, 0, ct, X, N, Np, n, m->Kinv, m->v, part + size_t(ng) * tiles);
+				generated[ng++] = 1 + d;
+			}
+		}
+		GPLE_LAUNCH(ctx, sum_rows_kernel, ng, 1024, 0, part, tiles, out + 4);
+	}
+	double h[16];
+	read_back(ctx, out, 4 + ng, h);
+	*value = 0.5 * h[1] + h[0];
+	if (grad != nullptr)
+	{
+		const double mag = m->theta[0], noise = m->theta[np - 1];
+		const double rows = double(m->is_complex ? 2 * N : N);
+		grad[0] = (rows - h[1]) / mag;
+		grad[np - 1] = (m->is_complex ? 0.5 : 1.0) * mag * mag * noise * (h[3] - h[2]);
+		for (int k = 0; k < ng; k++)
+		{
+			grad[generated[k]] = 0.5 * h[4 + k];
+		}
+	}
+}
 } // namespace gple

@@ -119,6 +119,13 @@ public:
 	const PhasePoints& get_left_feature() const { return Feature; }
 	double get_rescale_factor() const { return S.rescale; }
 	double get_magnitude() const { return S.magnitude; }
+	/// NLML / LLT objective of test/gpr.cpp:470-532 on this model; Gradient (4 entries) is filled when non-null
+	double get_negative_log_marginal_likelihood(ParameterArray<double>* Gradient = nullptr) const
+	{
+		double v = 0.0;
+		Context::check(gple_model_nlml(Context::get(), Handle.get(), &v, Gradient != nullptr ? Gradient->data() : nullptr), "nlml");
+		return v;
+	}
 	double get_error() const { assert(Flags & GPLE_CALC_ERROR); return S.error; }
 	double get_population() const { assert(Flags & GPLE_CALC_AVERAGE); return S.population; }
 	ClassicalPhaseVector get_1st_order_average() const { assert(Flags & GPLE_CALC_AVERAGE); return {S.first_order[0], S.first_order[1]}; }
@@ -180,6 +187,8 @@ class TrainingComplexKernel
 {
 public:
 	static constexpr std::size_t NumTotalParameters = 8;
+	template <typename T>
+	using ParameterArray = std::array<T, NumTotalParameters>;
 	TrainingComplexKernel(const ParameterVector& Parameter, const ElementTrainingSet& TrainingSet, bool IsToCalculateError, bool IsToCalculateAverage, bool IsToCalculateDerivative):
 		Params(Parameter), N(std::get<0>(TrainingSet).cols()),
 		Flags((IsToCalculateError ? GPLE_CALC_ERROR : 0u) | (IsToCalculateAverage ? GPLE_CALC_AVERAGE : 0u) | (IsToCalculateDerivative ? GPLE_CALC_DERIVATIVE : 0u))
@@ -193,6 +202,13 @@ public:
 	const ParameterVector& get_parameters() const { return Params; }
 	double get_rescale_factor() const { return S.rescale; }
 	double get_magnitude() const { return S.magnitude; }
+	/// NLML / LLT objective of test/gpr.cpp:470-532 on this model; Gradient (8 entries) is filled when non-null
+	double get_negative_log_marginal_likelihood(ParameterArray<double>* Gradient = nullptr) const
+	{
+		double v = 0.0;
+		Context::check(gple_model_nlml(Context::get(), Handle.get(), &v, Gradient != nullptr ? Gradient->data() : nullptr), "nlml");
+		return v;
+	}
 	double get_error() const { assert(Flags & GPLE_CALC_ERROR); return S.error; }
 	double get_purity() const { assert(Flags & GPLE_CALC_AVERAGE); return S.purity; }
 	std::vector<std::complex<double>> get_upper_left_block_of_augmented_inverse() const { return cfield(GPLE_FIELD_UPPER_LEFT, N * N); }

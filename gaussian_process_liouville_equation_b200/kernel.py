@@ -56,6 +56,13 @@ class TrainingKernel:
     def get_magnitude(self):
         return self._s.magnitude
 
+    def get_negative_log_marginal_likelihood(self, grad: bool = False):
+        """NLML / LLT objective of test/gpr.cpp:470-532 on this model (value, or (value, gradient[4]))."""
+        v = C.c_double()
+        g = np.empty(4) if grad else None
+        self.ctx.check(self.ctx.lib.gple_model_nlml(self.ctx.h, self.h, C.byref(v), L.addr(g) if grad else None))
+        return (v.value, g) if grad else v.value
+
     def _need(self, flag, what):
         assert self._flags & flag, f"{what} was not requested at construction (reference asserts has_value())"
 

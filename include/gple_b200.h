@@ -132,6 +132,13 @@ extern "C"
 	};
 	int gple_model_get(gple_ctx* ctx, const gple_model* model, int which, double* out);
 	int gple_model_is_complex(const gple_model* model);
+	/* Negative log marginal likelihood with LLT -- the objective of the reference's test programme
+	 * (test/gpr.cpp:470-532, formula :475-496) -- of a trained element, as an alternative loss on the same kernels:
+	 *   value = y'^T K^-1 y' / 2 + sum ln L_ii   (y' = the model's rescaled labels; the n/2 ln 2 pi constant is dropped),
+	 *   grad[p] = tr[(K^-1 - b b^T) dK/dtheta_p] / 2, b = K^-1 y'   (4 or 8 doubles; NULL: value only).
+	 * Complex element: the likelihood of the composite [Re f; Im f] process (complex_kernel.h:12-13), with the true
+	 * derivatives (the reference's complex derivative arrays lack sigma^2, complex_kernel.cpp:37-51). */
+	int gple_model_nlml(gple_ctx* ctx, gple_model* model, double* value, double* grad);
 	size_t gple_model_size(const gple_model* model);
 	int gple_model_destroy(gple_ctx* ctx, gple_model* model);
 

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- C entry points of the CPU oracle for ctypes (tests/, smoke(), and the
 // cpu_baseline / --impl reference legs of bench.py).  The product library never links this file.
 #include "gple_oracle_dynamics.hpp"
+#include "gple_oracle_nlml.hpp"
 
 #include <chrono>
 #include <cstring>
@@ -429,5 +430,16 @@ extern "C"
 			out_c[2 * k] = v.real();
 			out_c[2 * k + 1] = v.imag();
 		}
+	}
+	// ---- NLML / LLT objective (test/gpr.cpp:470-532) on the element models ------------------------------
+	/// grad: 4 doubles or NULL (the model must have been trained with deriv = 1 when grad is requested)
+	double orc_nlml_real(const void* h, double* grad)
+	{
+		return nlml_real(*static_cast<const TrainingKernel*>(h), grad);
+	}
+	/// grad: 8 doubles or NULL
+	double orc_nlml_complex(const void* h, double* grad)
+	{
+		return nlml_complex(*static_cast<const TrainingComplexKernel*>(h), grad);
 	}
 }

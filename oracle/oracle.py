@@ -138,6 +138,13 @@ class TrainingKernel:
         lib().orc_predict_real(self.h, _p(Xq), C.c_size_t(Q), _p(yq), int(deriv), _p(pred), _p(var), _p(cut), _p(err), _p(derr))
         return dict(pred=pred, var=var, cutoff=cut, error=err[0], derror=derr)
 
+    def nlml(self, grad=False):
+        """test/gpr.cpp:470-532 on this model's kernel and rescaled labels: value, or (value, grad[4])."""
+        lib().orc_nlml_real.restype = C.c_double
+        g = np.empty(4) if grad else None
+        v = lib().orc_nlml_real(self.h, _p(g))
+        return (v, g) if grad else v
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_free_real(self.h)
@@ -198,6 +205,13 @@ class TrainingComplexKernel:
         yq = None if yq is None else _c128(yq)
         lib().orc_predict_complex(self.h, _p(Xq), C.c_size_t(Q), None if yq is None else yq.ctypes.data_as(_dp), int(deriv), pred.ctypes.data_as(_dp), _p(var), cut.ctypes.data_as(_dp), _p(err), _p(derr))
         return dict(pred=pred, var=var, cutoff=cut, error=err[0], derror=derr)
+
+    def nlml(self, grad=False):
+        """NLML of the composite [Re f; Im f] process (oracle/gple_oracle_nlml.hpp): value, or (value, grad[8])."""
+        lib().orc_nlml_complex.restype = C.c_double
+        g = np.empty(8) if grad else None
+        v = lib().orc_nlml_complex(self.h, _p(g))
+        return (v, g) if grad else v
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -93,3 +93,15 @@ def test_gradients_parity(ck, oracle):
     vo, go = oracle.loose_function(THETA, X, y, Xq, yq, grad=True)
     assert val == pytest.approx(vo, rel=1e-8)
     assert np.abs(g - go).max() <= 1e-6 * np.abs(go).max()
+
+
+def test_nlml_objective_parity(ck, oracle):
+    """NLML of the composite [Re f; Im f] process with its true gradient (oracle/gple_oracle_nlml.hpp)."""
+    X, y = syn.training_set(42, 1, 200)
+    th = np.array([1.3, 1.2, 0.8 * syn.SIGMA_X, 1.1 * syn.SIGMA_P, 0.7, 1.1 * syn.SIGMA_X, 0.9 * syn.SIGMA_P, 2e-2])
+    k = ck.TrainingComplexKernel(th, (X, y))
+    o = oracle.TrainingComplexKernel(th, X, y, deriv=True)
+    ov, og = o.nlml(grad=True)
+    v, g = k.get_negative_log_marginal_likelihood(grad=True)
+    assert v == pytest.approx(ov, rel=1e-9)
+    assert np.abs(g - og).max() <= 1e-7 * np.abs(og).max()

@@ -196,3 +196,16 @@ def test_argument_errors_are_status_codes(gk):
     assert ctx.lib.gple_predict_complex(ctx.h, k.h, L.addr(X), 2, None, L.addr(out), None, None, None, None) == L.ERR_ARG  # wrong kind
     assert ctx.lib.gple_predict_real(ctx.h, k.h, L.addr(X), 0, None, L.addr(out), None, None, None, None) == L.ERR_ARG  # no query
     assert b"model kind" in ctx.lib.gple_last_error(ctx.h) or b"query" in ctx.lib.gple_last_error(ctx.h)
+
+
+def test_nlml_objective_parity(gk, oracle):
+    """gple_model_nlml (the NLML / LLT objective of test/gpr.cpp:470-532) against the oracle: value 1e-9, gradient 1e-7."""
+    X, y = syn.training_set(41, 0, 300)
+    th = syn.theta_real() * np.array([1.1, 1.0, 1.0, 3.0])
+    k = gk.TrainingKernel(th, (X, y))
+    o = oracle.TrainingKernel(th, X, y, deriv=True)
+    ov, og = o.nlml(grad=True)
+    v, g = k.get_negative_log_marginal_likelihood(grad=True)
+    assert v == pytest.approx(ov, rel=1e-9)
+    assert np.abs(g - og).max() <= 1e-7 * np.abs(og).max()
+    assert k.get_negative_log_marginal_likelihood() == v
