@@ -1099,7 +1099,7 @@ void ensure_full_inverse(gple_ctx* ctx, gple_model* m)
 		return;
 	}
 	const int n = m->n;
-	m->Kinv = static_cast<double*>(ctx->pool.alloc(size_t(n) * n * sizeof(double)));
+	m->Kinv = static_cast<double*>((m->owner != nullptr ? m->owner : ctx)->pool.alloc(size_t(n) * n * sizeof(double))); // freed through the owner's pool
 	double* U = ctx->ws.get<double>("inv.U", size_t(n) * n);
 	GPLE_LAUNCH(ctx, transpose_kernel, dim3(n / 32, n / 32), dim3(32, 8), 0, m->W, U, n);
 	gemm::GemmArgs g{};

@@ -13,9 +13,11 @@
 #pragma once
 #include "../../include/gple_b200.h"
 
+#include <algorithm>
 #include <array>
 #include <cassert>
 #include <complex>
+#include <future>
 #include <limits>
 #include <memory>
 #include <optional>
@@ -53,13 +55,22 @@ static_assert(sizeof(PhaseSpacePoint) == 32, "PhaseSpacePoint must stay the refe
 using ElementPoints = std::vector<PhaseSpacePoint>;			 // gple/storage.h:327
 using AllPoints = std::array<ElementPoints, NumElements>;	 // lower-triangular order rho00, rho10, rho11
 
+/// One library context (CUDA stream + workspace) per worker slot.  The C-ABI is thread-safe across contexts, so the
+/// independent element models of a step / of a loss evaluation are built concurrently, each on the context of its slot
+/// (ContextSlot sets the slot of the calling thread).  Slot 0 is the main context.
 class Context
 {
 public:
+	static constexpr int NumSlots = 3;
+	static int& slot()
+	{
+		static thread_local int s = 0;
+		return s;
+	}
 	static gple_ctx* get(int device = 0)
 	{
 		static Context c(device);
-		return c.ctx;
+		return c.ctx[slot()];
 	}
 	static void check(int rc, const char* where, bool allow_not_spd = false)
 	{
@@ -71,16 +82,58 @@ public:
 	}
 
 private:
-	gple_ctx* ctx = nullptr;
+	gple_ctx* ctx[NumSlots] = {nullptr, nullptr, nullptr};
 	explicit Context(int device)
 	{
-		if (gple_ctx_create(device, &ctx) != GPLE_OK)
+		for (auto& c : ctx)
 		{
-			throw std::runtime_error("gple_ctx_create failed: no CUDA device (there is no CPU fallback)");
+			if (gple_ctx_create(device, &c) != GPLE_OK)
+			{
+				throw std::runtime_error("gple_ctx_create failed: no CUDA device (there is no CPU fallback)");
+			}
 		}
 	}
-	~Context() { gple_ctx_destroy(ctx); }
+	~Context()
+	{
+		for (auto& c : ctx)
+		{
+			gple_ctx_destroy(c);
+		}
+	}
 };
+
+/// RAII: the calling thread uses the context of slot k until the guard goes out of scope
+struct ContextSlot
+{
+	int previous;
+	explicit ContextSlot(const int k): previous(Context::slot()) { Context::slot() = k % Context::NumSlots; }
+	~ContextSlot() { Context::slot() = previous; }
+	ContextSlot(const ContextSlot&) = delete;
+	ContextSlot& operator=(const ContextSlot&) = delete;
+};
+
+/// Run f(0), f(1), f(2) concurrently, f(k) on the context of slot k; exceptions are re-thrown in the caller.
+template <typename F>
+inline void for_each_element_concurrently(F&& f)
+{
+	std::array<std::future<void>, 2> others;
+	for (int k = 1; k < 3; k++)
+	{
+		others[k - 1] = std::async(
+			std::launch::async,
+			[&f, k]()
+			{
+				const ContextSlot guard(k);
+				f(std::size_t(k));
+			}
+		);
+	}
+	f(std::size_t(0));
+	for (auto& o : others)
+	{
+		o.get();
+	}
+}
 
 struct ModelDeleter
 {
@@ -211,6 +264,8 @@ public:
 	}
 	double get_error() const { assert(Flags & GPLE_CALC_ERROR); return S.error; }
 	double get_purity() const { assert(Flags & GPLE_CALC_AVERAGE); return S.purity; }
+	ParameterArray<double> get_error_derivative() const { return arr(S.d_error); }
+	ParameterArray<double> get_purity_derivative() const { return arr(S.d_purity); }
 	std::vector<std::complex<double>> get_upper_left_block_of_augmented_inverse() const { return cfield(GPLE_FIELD_UPPER_LEFT, N * N); }
 	std::vector<std::complex<double>> get_lower_left_block_of_augmented_inverse() const { return cfield(GPLE_FIELD_LOWER_LEFT, N * N); }
 	std::vector<std::complex<double>> get_upper_part_of_augmented_inverse_times_label() const { return cfield(GPLE_FIELD_INV_LABEL, N); }
@@ -224,6 +279,7 @@ private:
 	int Status = GPLE_OK;
 	gple_complex_scalars S{};
 	ModelHandle Handle;
+	static ParameterArray<double> arr(const double* p) { return {p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]}; }
 	std::vector<std::complex<double>> cfield(int which, std::size_t count) const
 	{
 		std::vector<std::complex<double>> out(count);
@@ -254,35 +310,59 @@ private:
 	double Error = std::numeric_limits<double>::quiet_NaN();
 };
 
-/// gple/predict.h:89-143 -- the (up to) three element models of one time step
+using AllTrainingSets = std::array<ElementTrainingSet, NumElements>; // gple/predict.h:14 (lower-triangular order rho00, rho10, rho11)
+
+/// construct_training_sets (gple/predict.cpp:246-280): AoS points -> (2 x n features, n complex labels) per element
+inline AllTrainingSets construct_training_sets(const AllPoints& density)
+{
+	AllTrainingSets result;
+	for (std::size_t e = 0; e < NumElements; e++)
+	{
+		const std::size_t n = density[e].size();
+		result[e] = ElementTrainingSet{PhasePoints(n), std::vector<std::complex<double>>(n)};
+		for (std::size_t i = 0; i < n; i++)
+		{
+			std::get<0>(result[e])(0, i) = density[e][i].r[0];
+			std::get<0>(result[e])(1, i) = density[e][i].r[1];
+			std::get<1>(result[e])[i] = density[e][i].rho;
+		}
+	}
+	return result;
+}
+
+/// gple/predict.h:89-143 -- the (up to) three element models of one time step; the three factorisations run concurrently
 class TrainingKernels
 {
 public:
-	/// gple/predict.cpp:390-393 (error = true, average = true, derivative = false); empty elements stay nullopt
-	TrainingKernels(const std::array<ParameterVector, NumElements>& ParameterVectors, const AllPoints& density)
+	static constexpr std::size_t NumTotalParameters = 4 * NumPES + 8; // gple/predict.h:17
+	using QuantumVectorD = std::array<double, NumPES>;
+
+	/// gple/predict.cpp:362-388; an element stays nullopt when its training set is empty or all its parameters are 0 (:339-357)
+	TrainingKernels(const std::array<ParameterVector, NumElements>& ParameterVectors, const AllTrainingSets& TrainingSets, bool IsToCalculateError, bool IsToCalculateAverage, bool IsToCalculateDerivative)
 	{
-		for (std::size_t e = 0; e < NumElements; e++)
-		{
-			if (density[e].empty())
+		for_each_element_concurrently(
+			[&](const std::size_t e)
 			{
-				continue;
+				const bool all_zero = std::all_of(ParameterVectors[e].cbegin(), ParameterVectors[e].cend(), [](double d) { return d == 0.0; });
+				if (std::get<0>(TrainingSets[e]).cols() == 0 || all_zero)
+				{
+					return;
+				}
+				if (e == 1)
+				{
+					OffDiagonal.emplace(ParameterVectors[e], TrainingSets[e], IsToCalculateError, IsToCalculateAverage, IsToCalculateDerivative);
+				}
+				else
+				{
+					Diagonal[e / 2].emplace(ParameterVectors[e], TrainingSets[e], IsToCalculateError, IsToCalculateAverage, IsToCalculateDerivative);
+				}
 			}
-			ElementTrainingSet ts{PhasePoints(density[e].size()), std::vector<std::complex<double>>(density[e].size())};
-			for (std::size_t i = 0; i < density[e].size(); i++) // gple/predict.cpp:246-280
-			{
-				std::get<0>(ts)(0, i) = density[e][i].r[0];
-				std::get<0>(ts)(1, i) = density[e][i].r[1];
-				std::get<1>(ts)[i] = density[e][i].rho;
-			}
-			if (e == 1)
-			{
-				OffDiagonal.emplace(ParameterVectors[e], ts, true, true, false);
-			}
-			else
-			{
-				Diagonal[e / 2].emplace(ParameterVectors[e], ts, true, true, false);
-			}
-		}
+		);
+	}
+	/// gple/predict.cpp:390-393 (error = true, average = true, derivative = false)
+	TrainingKernels(const std::array<ParameterVector, NumElements>& ParameterVectors, const AllPoints& density):
+		TrainingKernels(ParameterVectors, construct_training_sets(density), true, true, false)
+	{
 	}
 	double calculate_population() const // gple/predict.cpp:395-406
 	{
@@ -293,12 +373,83 @@ public:
 		}
 		return r;
 	}
+	ClassicalPhaseVector calculate_1st_order_average() const // gple/predict.cpp:408-419
+	{
+		ClassicalPhaseVector r{0.0, 0.0};
+		for (const auto& k : Diagonal)
+		{
+			if (k)
+			{
+				const ClassicalPhaseVector a = k->get_1st_order_average();
+				r[0] += a[0];
+				r[1] += a[1];
+			}
+		}
+		return r;
+	}
+	double calculate_total_energy_average(const QuantumVectorD& Energies) const // gple/predict.cpp:423-436
+	{
+		double r = 0.0;
+		for (std::size_t i = 0; i < NumPES; i++)
+		{
+			r += Diagonal[i] ? Diagonal[i]->get_population() * Energies[i] : 0.0;
+		}
+		return r;
+	}
 	double calculate_purity() const // gple/predict.cpp:439-463
 	{
 		double r = OffDiagonal ? 2.0 * OffDiagonal->get_purity() : 0.0;
 		for (const auto& k : Diagonal)
 		{
 			r += k ? k->get_purity() : 0.0;
+		}
+		return r;
+	}
+	/// gple/predict.cpp:465-484: diagonal parameters only (2 x 4)
+	ParameterVector population_derivative() const
+	{
+		ParameterVector r(4 * NumPES, 0.0);
+		for (std::size_t i = 0; i < NumPES; i++)
+		{
+			if (Diagonal[i])
+			{
+				const auto d = Diagonal[i]->get_population_derivative();
+				std::copy(d.cbegin(), d.cend(), r.begin() + 4 * i);
+			}
+		}
+		return r;
+	}
+	/// gple/predict.cpp:486-510
+	ParameterVector total_energy_derivative(const QuantumVectorD& Energies) const
+	{
+		ParameterVector r = population_derivative();
+		for (std::size_t i = 0; i < NumPES; i++)
+		{
+			for (std::size_t p = 0; p < 4; p++)
+			{
+				r[4 * i + p] *= Energies[i];
+			}
+		}
+		return r;
+	}
+	/// gple/predict.cpp:512-559: all 16 parameters in element order, the off-diagonal element weighted by 2
+	ParameterVector purity_derivative() const
+	{
+		ParameterVector r(NumTotalParameters, 0.0);
+		if (Diagonal[0])
+		{
+			const auto d = Diagonal[0]->get_purity_derivative();
+			std::copy(d.cbegin(), d.cend(), r.begin());
+		}
+		if (OffDiagonal)
+		{
+			const auto d = OffDiagonal->get_purity_derivative();
+			std::transform(d.cbegin(), d.cend(), r.begin() + 4, [](double x) { return 2.0 * x; });
+		}
+		if (Diagonal[1])
+		{
+			const auto d = Diagonal[1]->get_purity_derivative();
+			std::copy(d.cbegin(), d.cend(), r.begin() + 12);
 		}
 		return r;
 	}

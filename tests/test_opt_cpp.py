@@ -1,0 +1,102 @@
+"""The C++ optimiser mirror (host/gple_opt.hpp + host/nlopt_lite.hpp).
+
+CPU: nlopt_lite reaches the known optima of analytic problems; gple_opt.hpp compiles and links against the C-ABI.
+GPU: Optimization::optimize on a C1-like case reaches an outcome as good as the scipy-based Python driver run on the
+oracle's callbacks (parity on outcomes), and on a three-element case stays within its bounds with all
+elements optimised concurrently."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from gaussian_process_liouville_equation_b200 import synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "cpp", "_build")
+LIBDIR = os.path.join(ROOT, "gaussian_process_liouville_equation_b200")
+
+
+def compile_cpp(name, link):
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, name)
+    cmd = ["g++", "-std=c++20", "-O2", "-Wall", "-Wextra", "-pthread", os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe]
+    if link:
+        cmd += [f"-L{LIBDIR}", "-lgple_b200", f"-Wl,-rpath,{LIBDIR}"]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_nlopt_lite_on_analytic_problems():
+    exe = compile_cpp("nlopt_lite_test", link=False)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "FAIL" not in r.stdout, r.stdout
+
+
+def test_optimiser_mirror_compiles_and_links():
+    assert os.path.exists(compile_cpp("opt_test", link=True))
+
+
+def write_points(path, density, extra):
+    with open(path, "w") as f:
+        for group in (density, extra):
+            for pts in group:
+                if pts is None:
+                    f.write("0\n")
+                    continue
+                f.write(f"{len(pts)}\n")
+                for row in pts:
+                    f.write(" ".join(repr(float(v)) for v in row) + "\n")
+
+
+def run_cpp(density, extra, pes_model, e0, purity, tmp_path, *caps):
+    exe = compile_cpp("opt_test", link=True)
+    path = os.path.join(tmp_path, "points.txt")
+    write_points(path, density, extra)
+    out = subprocess.run([exe, path, str(pes_model), repr(syn.MASS), repr(e0), repr(purity), *map(str, caps)], capture_output=True, text=True, check=True).stdout
+    return {k: float(v) for k, v in (line.split() for line in out.strip().splitlines())}
+
+
+@pytest.mark.gpu
+def test_cpp_optimiser_matches_python_driver_outcome(tmp_path):
+    import oracle_backend
+    from gaussian_process_liouville_equation_b200 import opt, predict
+
+    n = 48
+    X, y = syn.training_set(61, 0, n, (syn.X0, syn.P0))
+    y = y / 0.6  # population 1, purity 1
+    Xe, ye = syn.extra_points(61, 0, X, 5 * n, (syn.X0, syn.P0))
+    density, extra = [syn.points_aos(X, y), None, None], [syn.points_aos(Xe, ye / 0.6), None, None]
+    o = oracle_backend.observable_sums(0, density[0], syn.MASS, 0)
+    e0 = o[7] / o[0]
+    got = run_cpp(density, extra, 0, e0, 1.0, str(tmp_path))
+    ref = opt.Optimization((syn.SIGMA_X, syn.SIGMA_P), syn.MASS, 0, InitialTotalEnergy=e0, InitialPurity=1.0, backend=oracle_backend, max_global_evals=200)
+    (err, steps, typ), check = ref.optimize(density, extra)
+    k = predict.TrainingKernels(ref.get_parameters(), predict.construct_training_sets(density), True, True, False, oracle_backend)
+    # outcomes: the C++ driver ends at a loss no worse than 1.5x the scipy driver's, with the averages as close to their targets
+    assert np.isfinite(got["error"]) and got["error"] <= 1.5 * err + 1e-12
+    assert abs(got["population"] - 1.0) <= max(2 * opt.AverageTolerance, 1.5 * abs(k.calculate_population() - 1.0))
+    assert abs(got["purity"] - 1.0) <= max(2 * opt.AverageTolerance, 1.5 * abs(k.calculate_purity() - 1.0))
+    assert got["lb0_1"] <= got["theta0_1"] <= got["ub0_1"] and got["theta0_3"] == opt.InitialNoise
+    assert got["steps0"] > 10 and got["evaluations"] > got["steps0"]
+
+
+@pytest.mark.gpu
+def test_cpp_optimiser_three_elements(tmp_path):
+    n, centre = 64, (0.0, syn.P0)
+    density, extra = [], []
+    for e in range(3):
+        X, y = syn.training_set(63, e, n, centre)
+        Xe, ye = syn.extra_points(63, e, X, 5 * n, centre)
+        density.append(syn.points_aos(X, y))
+        extra.append(syn.points_aos(Xe, ye))
+    import oracle_backend
+
+    o = [oracle_backend.observable_sums(1, density[e], syn.MASS, i) for i, e in enumerate((0, 2))]
+    e0 = 0.6 * o[0][7] / o[0][0] + 0.4 * o[1][7] / o[1][0]
+    got = run_cpp(density, extra, 1, e0, 1.0, str(tmp_path), 100, 300)
+    assert np.isfinite(got["error"]) and got["error"] >= 0.0
+    assert abs(got["population"] - 1.0) < 0.2 and abs(got["energy"] / e0 - 1.0) < 0.2
+    for e, npar in enumerate((4, 8, 4)):
+        assert all(np.isfinite(got[f"theta{e}_{p}"]) for p in range(npar))
+    assert got["steps0"] > 0 and got["steps1"] > 0 and got["steps2"] > 0 and got["steps4"] > 0
