@@ -45,7 +45,6 @@ WORKLOAD = ("C2: Tully SAC, N=2048 training points/element, 3 elements (rho00,rh
             "step = TrainingKernels rebuild (3 elements) + evolve (8Q GPR predictions per element)")
 
 
-
 def make_inputs():
     sets = [syn.training_set(2, e, N_TRAIN, CENTRE) for e in range(3)]
     pts = []
@@ -349,7 +348,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2 (default, BASELINE.json configs[1]); c4 = configs[3]: ECR, N=4096, 1e6 evolved points/element, meant for --gpus 8")
     args = ap.parse_args()
+    if args.workload == "c4":
+        global N_TRAIN, Q_POINTS, PES_MODEL, WORKLOAD, THETA_R, THETA_C
+        N_TRAIN, Q_POINTS, PES_MODEL = 4096, 1_000_000, 2
+        scale = (2048.0 / N_TRAIN) ** 0.5  # lengths shrink with N: comparable conditioning (allowed by the bounds of opt.cpp:1036-1040)
+        THETA_R = syn.theta_real(scale)
+        THETA_C = THETA_C * np.array([1, 1, scale, scale, 1, scale, scale, 1])
+        WORKLOAD = ("C4: Tully extended coupling with reflection, N=4096 training points/element, 3 elements, Q=1e6 evolved MC points/element/step "
+                    "sharded over the GPUs; step = TrainingKernels rebuild (3 elements) + evolve (8Q GPR predictions per element)")
+        args.no_cpu_baseline = True  # the CPU sample is sized for C2
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -51,6 +51,13 @@ def labels(element_id: int, r: np.ndarray, centre) -> np.ndarray:
     return np.sqrt(g00 * g11) * np.exp(1j * phase)
 
 
+def snapshot_purity() -> float:
+    """Purity of the three-element synthetic snapshot of `labels`: (2 pi hbar) int rho_ii^2 = pop_i^2 for the Wigner Gaussians
+    (sigma_x sigma_p = hbar / 2) plus 2 (2 pi hbar) int |rho10|^2 = 2 * 0.24 * overlap of the two shifted Gaussians."""
+    overlap = np.exp(-(0.5 ** 2) / (4.0 * SIGMA_X ** 2) - (0.3 ** 2) / (4.0 * SIGMA_P ** 2))
+    return 0.6 ** 2 + 0.4 ** 2 + 2.0 * 0.24 * overlap
+
+
 def training_set(config_id: int, element_id: int, n: int, centre=(0.0, P0)):
     """N i.i.d. features x ~ N(x_c, sigma_x^2), p ~ N(p_c, sigma_p^2) and their labels.
 

@@ -47,7 +47,7 @@ for N in SIZES:
 
     dynamics.loose_function = counted_lf
     opt.pr.TrainingKernels = counted_tk
-    optimizer = opt.Optimization((syn.SIGMA_X, syn.SIGMA_P), syn.MASS, DAC, InitialTotalEnergy=e_tot, InitialPurity=0.6 ** 2 + 0.4 ** 2 + 2 * 0.24, max_global_evals=300)
+    optimizer = opt.Optimization((syn.SIGMA_X, syn.SIGMA_P), syn.MASS, DAC, InitialTotalEnergy=e_tot, InitialPurity=syn.snapshot_purity(), max_global_evals=300)
     launches0 = ctx.launches
     ctx.sync()
     t = time.perf_counter()
