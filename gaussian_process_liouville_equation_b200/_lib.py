@@ -62,6 +62,7 @@ SIGNATURES = {
     "gple_new_point_predict": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),
     "gple_observables": (C.c_int, [_vp, C.c_int, _dp, _sz, C.c_double, C.c_int, _dp]),
     "gple_tune_variance_gemm": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "gple_set_potrf_flat": (C.c_int, [C.c_int]),
     "gple_set_variance_gemm_variant": (C.c_int, [C.c_int]),
     "gple_profile_enable": (C.c_int, [_vp, C.c_int]),
     "gple_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),

@@ -685,6 +685,10 @@ extern "C"
 		);
 	}
 
+	int gple_set_potrf_flat(int n)
+	{
+		return set_potrf_flat(n < 128 ? 128 : n);
+	}
 	int gple_set_variance_gemm_variant(int variant)
 	{
 		return set_variance_gemm_variant(variant) == 0 ? GPLE_OK : GPLE_ERR_ARG;

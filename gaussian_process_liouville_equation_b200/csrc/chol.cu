@@ -335,11 +335,19 @@ void run_gemm(gple_ctx* ctx, bool b_nn, const gemm::GemmArgs& a)
 		return;
 	}
 	// 128 x 128 tiles once they fill at least about half of the SMs, 64 x 64 tiles below that (latency-bound regime)
-	const long long tiles128 = (long long)(a.N / 128) * (a.M / 128) / (a.lower_only ? 2 : 1);
+	const unsigned nz = unsigned(a.batch > 1 ? a.batch : 1);
+	if (a.in_place && !b_nn && a.N == 128 && a.M / 128 * 2 < ctx->num_sms)
+	{
+		// panel solve with few row blocks: 32-row strips quarter the per-CTA latency (a 128 x 128 x 128 tile is 17 us of DMMA)
+		using C = gemm::StripConfig;
+		GPLE_LAUNCH(ctx, (gemm::gemm_kernel<C, false>), dim3(1, a.M / C::BM, nz), C::THREADS, C::SMEM_BYTES, a);
+		return;
+	}
+	const long long tiles128 = (long long)(a.N / 128) * (a.M / 128) / (a.lower_only ? 2 : 1) * nz;
 	if (tiles128 * 2 >= ctx->num_sms || a.in_place)
 	{
 		using C = gemm::DefaultConfig;
-		const dim3 grid(a.N / C::BN, a.M / C::BM);
+		const dim3 grid(a.N / C::BN, a.M / C::BM, nz);
 		if (b_nn)
 		{
 			GPLE_LAUNCH(ctx, (gemm::gemm_kernel<C, true>), grid, C::THREADS, C::SMEM_BYTES, a);
@@ -352,7 +360,7 @@ void run_gemm(gple_ctx* ctx, bool b_nn, const gemm::GemmArgs& a)
 	else
 	{
 		using C = gemm::SmallConfig;
-		const dim3 grid(a.N / C::BN, a.M / C::BM);
+		const dim3 grid(a.N / C::BN, a.M / C::BM, nz);
 		if (b_nn)
 		{
 			GPLE_LAUNCH(ctx, (gemm::gemm_kernel<C, true>), grid, C::THREADS, C::SMEM_BYTES, a);
@@ -363,6 +371,9 @@ void run_gemm(gple_ctx* ctx, bool b_nn, const gemm::GemmArgs& a)
 		}
 	}
 }
+
+/// potrf switches from the recursive form to the right-looking sweep at or below this block size (gple_set_potrf_flat)
+int g_potrf_flat = 4096; // profiles/r01_tune_potrf.md
 
 int split(const int n)
 {
@@ -417,11 +428,48 @@ struct Chol
 		trsm(r0, m, c0 + n1, n2);
 	}
 
+	void leaf(const int o) const
+	{
+		GPLE_LAUNCH(ctx, potrf_leaf_kernel, 1, LEAF_THREADS, LEAF_SMEM, at(o, o), ld, dinv + size_t(o / LEAF) * LEAF * LEAF, info, o);
+	}
+
+	/// Right-looking sweep over 128-blocks (every GEMM has K = 128): the latency-optimal order for blocks of up to a few
+	/// thousand rows, where the recursive form leaves most SMs idle behind a few long-K tiles.
+	void potrf_flat(const int o, const int n) const
+	{
+		for (int k = 0; k < n; k += LEAF)
+		{
+			leaf(o + k);
+			const int rest = n - k - LEAF;
+			if (rest > 0)
+			{
+				trsm(o + k + LEAF, rest, o + k, LEAF);
+				gemm::GemmArgs g{};
+				g.A = at(o + k + LEAF, o + k);
+				g.B = at(o + k + LEAF, o + k);
+				g.C = at(o + k + LEAF, o + k + LEAF);
+				g.lda = g.ldb = g.ldc = ld;
+				g.M = rest;
+				g.N = rest;
+				g.K = LEAF;
+				g.alpha = -1.0;
+				g.beta = 1.0;
+				g.lower_only = 1;
+				run_gemm(ctx, false, g);
+			}
+		}
+	}
+
 	void potrf(const int o, const int n) const
 	{
 		if (n == LEAF)
 		{
-			GPLE_LAUNCH(ctx, potrf_leaf_kernel, 1, LEAF_THREADS, LEAF_SMEM, at(o, o), ld, dinv + size_t(o / LEAF) * LEAF * LEAF, info, o);
+			leaf(o);
+			return;
+		}
+		if (n <= g_potrf_flat)
+		{
+			potrf_flat(o, n);
 			return;
 		}
 		const int n1 = split(n), n2 = n - n1;
@@ -442,46 +490,68 @@ struct Chol
 		potrf(o + n1, n2);
 	}
 
-	/// W (same layout, zero-initialised with the inverted diagonal blocks in place) <- L^-1
-	void trtri(double* W, double* T, const int o, const int n) const
+	/// W (same layout, zero-initialised with the inverted diagonal blocks in place) <- L^-1, bottom-up: at block size
+	/// b = 128, 256, ... every pair of adjacent b-blocks [o, o + b), [o + b, o + b + n2) is combined,
+	///     T = L21 W11 ;  W21 = -W22 T ,
+	/// all pairs of a level in ONE batched launch per product (they are independent), so the whole inverse takes
+	/// 2 log2(n / 128) launches that fill the chip instead of 2 (n / 128 - 1) small dependent ones.  A ragged last pair
+	/// (n2 < b) gets its own launch.
+	void trtri(double* W, double* T) const
 	{
-		if (n == LEAF)
+		const int n = int(ld);
+		for (int b = LEAF; b < n; b *= 2)
 		{
-			return;
+			const int full = n / (2 * b);						// pairs with two complete b-blocks
+			const int tail = n - full * 2 * b;					// rows left over after them
+			const int ragged_n2 = tail > b ? tail - b : 0;		// a last pair (b, ragged_n2) exists iff tail > b
+			auto combine = [&](const int o, const int n2, const int batch)
+			{
+				// T (n2 x b) = L21 * W11   (NN; W11[k][j] == 0 for j > k)
+				gemm::GemmArgs g{};
+				g.A = at(o + b, o);
+				g.B = W + size_t(o) * ld + o;
+				g.C = T;
+				g.lda = ld;
+				g.ldb = ld;
+				g.ldc = size_t(b);
+				g.M = n2;
+				g.N = b;
+				g.K = b;
+				g.alpha = 1.0;
+				g.beta = 0.0;
+				g.tri = gemm::B_LOWER_NN;
+				g.batch = batch;
+				g.strideA = g.strideB = size_t(2 * b) * ld + size_t(2 * b);
+				g.strideC = size_t(b) * b;
+				run_gemm(ctx, true, g);
+				// W21 = -W22 * T            (NN; W22[i][k] == 0 for k > i)
+				gemm::GemmArgs h{};
+				h.A = W + size_t(o + b) * ld + o + b;
+				h.B = T;
+				h.C = W + size_t(o + b) * ld + o;
+				h.lda = ld;
+				h.ldb = size_t(b);
+				h.ldc = ld;
+				h.M = n2;
+				h.N = b;
+				h.K = n2;
+				h.alpha = -1.0;
+				h.beta = 0.0;
+				h.tri = gemm::A_LOWER;
+				h.batch = batch;
+				h.strideA = h.strideC = size_t(2 * b) * ld + size_t(2 * b);
+				h.strideB = size_t(b) * b;
+				run_gemm(ctx, true, h);
+			};
+			if (full > 0)
+			{
+				combine(0, b, full);
+			}
+			if (ragged_n2 > 0)
+			{
+				combine(full * 2 * b, ragged_n2, 1);
+			}
 		}
-		const int n1 = split(n), n2 = n - n1;
-		trtri(W, T, o, n1);
-		trtri(W, T, o + n1, n2);
-		// T (n2 x n1) = L21 * W11   (NN; W11[k][j] == 0 for j > k)
-		gemm::GemmArgs g{};
-		g.A = at(o + n1, o);
-		g.B = W + size_t(o) * ld + o;
-		g.C = T;
-		g.lda = ld;
-		g.ldb = ld;
-		g.ldc = size_t(n1);
-		g.M = n2;
-		g.N = n1;
-		g.K = n1;
-		g.alpha = 1.0;
-		g.beta = 0.0;
-		g.tri = gemm::B_LOWER_NN;
-		run_gemm(ctx, true, g);
-		// W21 = -W22 * T            (NN; W22[i][k] == 0 for k > i)
-		gemm::GemmArgs h{};
-		h.A = W + size_t(o + n1) * ld + o + n1;
-		h.B = T;
-		h.C = W + size_t(o + n1) * ld + o;
-		h.lda = ld;
-		h.ldb = size_t(n1);
-		h.ldc = ld;
-		h.M = n2;
-		h.N = n1;
-		h.K = n2;
-		h.alpha = -1.0;
-		h.beta = 0.0;
-		h.tri = gemm::A_LOWER;
-		run_gemm(ctx, true, h);
 	}
 };
 } // namespace
@@ -497,6 +567,7 @@ void chol_setup_attributes()
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::DefaultConfig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::DefaultConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::SmallConfig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SmallConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::SmallConfig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SmallConfig::SMEM_BYTES)));
+	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::StripConfig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::StripConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LEAF_SMEM)));
 	done = true;
 }
@@ -510,6 +581,13 @@ void gemm_nn(gple_ctx* ctx, const gemm::GemmArgs& a)
 {
 	chol_setup_attributes();
 	run_gemm(ctx, true, a);
+}
+
+int set_potrf_flat(const int n)
+{
+	const int old = g_potrf_flat;
+	g_potrf_flat = n;
+	return old;
 }
 
 void potrf_trtri(gple_ctx* ctx, double* A, double* W, const int n, int* d_info)
@@ -529,7 +607,7 @@ void potrf_trtri(gple_ctx* ctx, double* A, double* W, const int n, int* d_info)
 	{
 		GPLE_CUDA(cudaMemsetAsync(W, 0, size_t(n) * n * sizeof(double), ctx->stream));
 		GPLE_LAUNCH(ctx, copy_dinv_kernel, n / LEAF, 256, 0, dinv, W, ld);
-		c.trtri(W, T, 0, n);
+		c.trtri(W, T);
 	}
 }
 

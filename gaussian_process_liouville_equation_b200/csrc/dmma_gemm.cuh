@@ -41,6 +41,8 @@ using DefaultConfig = Config<16, 4, 2, 4>;
 /// ... and 64 x 64 tiles (4 warps, 4x more CTAs, 4x shorter per-tile latency) for the small, latency-bound
 /// GEMMs on the critical path of the recursive factorisation
 using SmallConfig = Config<16, 4, 2, 2, 64, 64>;
+/// 32-row strips of a 128-wide panel: the in-place panel solve A21 <- A21 L^-T (one CTA must own a whole row strip)
+using StripConfig = Config<16, 4, 1, 4, 32, 128>;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
@@ -164,6 +166,9 @@ struct GemmArgs
 	int tri;		// bitmask of Tri
 	int lower_only; // skip output tiles strictly above the diagonal (SYRK-style)
 	int in_place;	// C aliases A with N == 128: one CTA must own a whole row strip (forces the 128 x 128 tiling)
+	// batched form: blockIdx.z = item, operands advance by the strides (in doubles); batch <= 1: a single GEMM
+	int batch;
+	size_t strideA, strideB, strideC;
 };
 
 /// C = beta * C + alpha * A * op(B)
@@ -203,8 +208,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const GemmArgs p)
 		kb = max(kb, n0);
 	}
 	const int nk = ke > kb ? (ke - kb) / C::BK : 0;
-	const double* Ag = p.A + size_t(m0) * p.lda + kb;
-	const double* Bg = B_NN ? p.B + size_t(kb) * p.ldb + n0 : p.B + size_t(n0) * p.ldb + kb;
+	const size_t z = blockIdx.z;
+	const double* Ag = p.A + z * p.strideA + size_t(m0) * p.lda + kb;
+	const double* Bz = p.B + z * p.strideB;
+	const double* Bg = B_NN ? Bz + size_t(kb) * p.ldb + n0 : Bz + size_t(n0) * p.ldb + kb;
+	double* Cz = p.C + z * p.strideC;
 
 	double acc[C::MI][C::NJ][2];
 	zero_acc<C>(acc);
@@ -250,7 +258,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const GemmArgs p)
 		for (int j = 0; j < C::NJ; j++)
 		{
 			const int col = n0 + wn * C::WTN + j * 8 + 2 * t;
-			double2* dst = reinterpret_cast<double2*>(p.C + size_t(row) * p.ldc + col);
+			double2* dst = reinterpret_cast<double2*>(Cz + size_t(row) * p.ldc + col);
 			double2 v = make_double2(p.alpha * acc[i][j][0], p.alpha * acc[i][j][1]);
 			if (p.beta != 0.0)
 			{

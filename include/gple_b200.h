@@ -195,6 +195,9 @@ extern "C"
 	 * `rows` x n (both multiples of 128); gple_set_variance_gemm_variant selects the variant used by predictions. */
 	int gple_tune_variance_gemm(gple_ctx* ctx, int variant, int rows, int n, int iters, double* ms_per_launch);
 	int gple_set_variance_gemm_variant(int variant);
+	/* Factorisation schedule: blocks of at most `n` rows are factorised by a right-looking sweep over 128-blocks (short
+	 * K = 128 GEMMs, latency-optimal), larger ones recursively (long-K GEMMs, throughput-optimal).  Returns the old value. */
+	int gple_set_potrf_flat(int n);
 	/* Register-resident DMMA / DFMA loops: measured FP64 tensor and vector peaks of this GPU, in TFLOP/s. */
 	int gple_measure_fp64_peak(gple_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
 	/* DMMA rate of the GEMM's own register tile (8 warps / SM, 32 accumulators, 8 + 4 changing operands, no memory):
