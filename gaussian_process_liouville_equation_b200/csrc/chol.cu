@@ -22,10 +22,25 @@ constexpr int LEAF_THREADS = 256; // 8 warps
 constexpr int PW = 16;			 // panel width / inverse block size
 constexpr size_t LEAF_SMEM = (size_t(LEAF) * LP + 8 * 16 * 20) * sizeof(double);
 
+/// 1 / sqrt(d) for the pivots: single-precision MUFU seed + two Newton steps in FP64 (error ~1 ulp), a much shorter
+/// dependent chain than the library rsqrt(double); outside the float range it falls back to the library.
+__device__ __forceinline__ double fast_rsqrt(const double d)
+{
+	if (!(d > 1e-30 && d < 1e30))
+	{
+		return rsqrt(d);
+	}
+	double y = double(rsqrtf(float(d)));
+	const double h = 0.5 * d;
+	y = y * fma(-h * y, y, 1.5);
+	y = y * fma(-h * y, y, 1.5);
+	return y;
+}
+
 /// Factor one 128 x 128 diagonal block and invert the resulting triangle, entirely in shared memory.
-///   factor : right-looking with 16-wide panels -- the 16 x 16 diagonal block by one warp (registers + shuffles),
-///            the panel below by one independent row-wise triangular solve per thread (no barriers inside), and the
-///            rank-16 trailing update of the lower triangle by all warps on DMMA;
+///   factor : right-looking with 8-wide panels -- the 8 x 8 diagonal block factorised redundantly in the registers of
+///            every thread that owns a panel row (no shuffles, no barrier between block and panel), one row-wise
+///            triangular solve per thread, and the rank-8 trailing update of the lower triangle by all warps on DMMA;
 ///   inverse: X = L^-1 by 16 x 16 blocks -- diagonal blocks by forward substitution (16 lanes each), then block
 ///            sub-diagonal after sub-diagonal  X_ij = -X_ii sum_{k=j}^{i-1} L_ik X_kj  on DMMA, one warp per block.
 /// L lives in the lower triangle of S (row-major, pitch LP); X is kept TRANSPOSED in the strictly-upper part,
@@ -48,97 +63,113 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
 	__syncthreads();
 
 	// ---------------------------------------------------------------- factor
-	for (int p = 0; p < LEAF / PW; p++)
+	// Right-looking with 8-wide panels.  The 8 x 8 diagonal block is factorised REDUNDANTLY by every thread that needs it,
+	// entirely in registers (36 doubles, no shuffles, no barrier): the serial chain per column is rsqrt -> scale -> fma.
+	// The same thread then solves its own panel row against its register copy of L_d (8-step substitution, the pivots'
+	// reciprocals come for free from the factorisation), and all warps apply the rank-8 trailing update on DMMA.
+	// The factorised diagonal blocks are parked in `scratch` (nobody reads them during the sweep) and copied back at the end,
+	// so that no thread can overwrite a diagonal block another thread is still loading.
+	constexpr int FW = 8;
+	double* Ld = scratch; // [16 panels][8][8]
+	for (int p = 0; p < LEAF / FW; p++)
 	{
-		const int c0 = p * PW;
-		if (warp == 0)
+		const int c0 = p * FW;
+		const int rows_below = LEAF - c0 - FW;
+		if (tid < rows_below || tid == LEAF_THREADS - 1)
 		{
-			// 16 x 16 diagonal block: lane i (< 16) owns row i in registers
-			const int i = lane & 15;
-			double a[PW];
+			double l[FW][FW], rs[FW];
 #pragma unroll
-			for (int k = 0; k < PW; k++)
+			for (int i = 0; i < FW; i++)
 			{
-				a[k] = (k <= i) ? S[(c0 + i) * LP + c0 + k] : 0.0;
+#pragma unroll
+				for (int k = 0; k <= i; k++)
+				{
+					l[i][k] = S[(c0 + i) * LP + c0 + k];
+				}
 			}
+			bool bad = false;
 #pragma unroll
-			for (int j = 0; j < PW; j++)
+			for (int j = 0; j < FW; j++)
 			{
-				double d = __shfl_sync(0xffffffffu, a[j], j);
+				double d = l[j][j];
 				if (!(d > 0.0))
 				{
-					if (lane == 0)
+					if (!bad && tid == LEAF_THREADS - 1)
 					{
 						atomicCAS(info, 0, global_row0 + c0 + j + 1);
 					}
+					bad = true;
 					d = 1.0;
 				}
-				const double rs = rsqrt(d), sd = d * rs; // one reciprocal square root instead of sqrt + division
-				const double l = (i == j) ? sd : a[j] * rs; // column j of L (rows >= j)
-				a[j] = l;
+				rs[j] = fast_rsqrt(d);
+				l[j][j] = d * rs[j];
 #pragma unroll
-				for (int k = j + 1; k < PW; k++)
+				for (int i = j + 1; i < FW; i++)
 				{
-					const double lk = __shfl_sync(0xffffffffu, l, k); // L[k][j]
-					if (i >= k)
+					l[i][j] *= rs[j];
+				}
+#pragma unroll
+				for (int k = j + 1; k < FW; k++)
+				{
+#pragma unroll
+					for (int i = k; i < FW; i++)
 					{
-						a[k] = fma(-l, lk, a[k]);
+						l[i][k] = fma(-l[i][j], l[k][j], l[i][k]);
 					}
 				}
 			}
-			if (lane < PW)
+			if (tid == LEAF_THREADS - 1)
 			{
 #pragma unroll
-				for (int k = 0; k < PW; k++)
+				for (int i = 0; i < FW; i++)
 				{
-					if (k <= i)
+#pragma unroll
+					for (int k = 0; k <= i; k++)
 					{
-						S[(c0 + i) * LP + c0 + k] = a[k];
+						Ld[p * FW * FW + i * FW + k] = l[i][k];
 					}
 				}
 			}
-		}
-		__syncthreads();
-		// panel below the diagonal block: row r solves x L_d^T = a (forward substitution, L_d broadcast from smem)
-		{
-			const int r = c0 + PW + tid;
-			if (tid < LEAF - c0 - PW)
+			else
 			{
-				double x[PW], rdiag[PW];
+				// panel row r: x L_d^T = a
+				const int r = c0 + FW + tid;
+				double x[FW];
 #pragma unroll
-				for (int k = 0; k < PW; k++)
+				for (int k = 0; k < FW; k += 2)
 				{
-					x[k] = S[r * LP + c0 + k];
-					rdiag[k] = 1.0 / S[(c0 + k) * LP + c0 + k]; // independent divisions, off the substitution chain
+					const double2 v = *reinterpret_cast<const double2*>(S + r * LP + c0 + k);
+					x[k] = v.x;
+					x[k + 1] = v.y;
 				}
 #pragma unroll
-				for (int j = 0; j < PW; j++)
+				for (int j = 0; j < FW; j++)
 				{
 					double v = x[j];
 #pragma unroll
 					for (int k = 0; k < j; k++)
 					{
-						v = fma(-x[k], S[(c0 + j) * LP + c0 + k], v);
+						v = fma(-x[k], l[j][k], v);
 					}
-					x[j] = v * rdiag[j];
+					x[j] = v * rs[j];
 				}
 #pragma unroll
-				for (int k = 0; k < PW; k++)
+				for (int k = 0; k < FW; k += 2)
 				{
-					S[r * LP + c0 + k] = x[k];
+					*reinterpret_cast<double2*>(S + r * LP + c0 + k) = make_double2(x[k], x[k + 1]);
 				}
 			}
 		}
 		__syncthreads();
-		// trailing update of the lower triangle: A22 -= P P^T, 8 x 8 tiles dealt round-robin to the warps
+		// trailing update of the lower triangle: A22 -= P P^T (k = 8), 8 x 8 tiles dealt round-robin to the warps
 		{
-			const int t0 = c0 + PW;			  // first trailing row / column
-			const int m = (LEAF - t0) / 8;	  // tile rows
+			const int t0 = c0 + FW;
+			const int m = (LEAF - t0) / 8;
 			const int ntiles = m * (m + 1) / 2;
 			for (int idx = warp; idx < ntiles; idx += LEAF_THREADS / 32)
 			{
 				// idx -> (ti, tj), tj <= ti
-				int ti = int((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+				int ti = int((sqrtf(8.0f * float(idx) + 1.0f) - 1.0f) * 0.5f);
 				while ((ti + 1) * (ti + 2) / 2 <= idx)
 				{
 					ti++;
@@ -153,7 +184,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
 				const double2 cv = *cptr;
 				double c[2] = {-cv.x, -cv.y}; // accumulate -(A22) + P P^T, negate back on store
 #pragma unroll
-				for (int kk = 0; kk < PW / 4; kk++)
+				for (int kk = 0; kk < FW / 4; kk++)
 				{
 					const double av = S[(r0 + g) * LP + c0 + kk * 4 + t];
 					const double bv = S[(q0 + g) * LP + c0 + kk * 4 + t];
@@ -164,6 +195,16 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
 		}
 		__syncthreads();
 	}
+	// factorised diagonal blocks back into place
+	for (int e = tid; e < (LEAF / FW) * FW * FW; e += LEAF_THREADS)
+	{
+		const int p = e / (FW * FW), i = (e / FW) % FW, k = e % FW;
+		if (k <= i)
+		{
+			S[(p * FW + i) * LP + p * FW + k] = Ld[e];
+		}
+	}
+	__syncthreads();
 
 	// ---------------------------------------------------------------- inverse
 	// diagonal 16 x 16 blocks: block i by lanes 0..15 of warp i; lane b owns column b of X_ii
