@@ -161,36 +161,50 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
 			}
 		}
 		__syncthreads();
-		// trailing update of the lower triangle: A22 -= P P^T (k = 8), 8 x 8 tiles dealt round-robin to the warps
+		// trailing update of the lower triangle: A22 -= P P^T (k = 8), 8 x 8 tiles dealt round-robin to the warps,
+		// two tiles in flight per warp (the load -> DMMA -> store chain of one tile is pure latency)
 		{
 			const int t0 = c0 + FW;
 			const int m = (LEAF - t0) / 8;
 			const int ntiles = m * (m + 1) / 2;
-			for (int idx = warp; idx < ntiles; idx += LEAF_THREADS / 32)
+			constexpr int NW = LEAF_THREADS / 32;
+			// tile idx -> (ti, tj), tj <= ti, advanced incrementally
+			int ti = 0, tj = warp;
+			auto normalise = [&]()
 			{
-				// idx -> (ti, tj), tj <= ti
-				int ti = int((sqrtf(8.0f * float(idx) + 1.0f) - 1.0f) * 0.5f);
-				while ((ti + 1) * (ti + 2) / 2 <= idx)
+				while (tj > ti)
 				{
+					tj -= ti + 1;
 					ti++;
 				}
-				while (ti * (ti + 1) / 2 > idx)
-				{
-					ti--;
-				}
-				const int tj = idx - ti * (ti + 1) / 2;
+			};
+			normalise();
+			for (int idx = warp; idx < ntiles; idx += 2 * NW)
+			{
 				const int r0 = t0 + ti * 8, q0 = t0 + tj * 8;
-				double2* cptr = reinterpret_cast<double2*>(S + (r0 + g) * LP + q0 + 2 * t);
-				const double2 cv = *cptr;
-				double c[2] = {-cv.x, -cv.y}; // accumulate -(A22) + P P^T, negate back on store
+				tj += NW;
+				normalise();
+				const bool second = idx + NW < ntiles;
+				const int r1 = second ? t0 + ti * 8 : r0, q1 = second ? t0 + tj * 8 : q0;
+				tj += NW;
+				normalise();
+				double2* cp0 = reinterpret_cast<double2*>(S + (r0 + g) * LP + q0 + 2 * t);
+				double2* cp1 = reinterpret_cast<double2*>(S + (r1 + g) * LP + q1 + 2 * t);
+				const double2 cv0 = *cp0, cv1 = *cp1;
+				double c0v[2] = {-cv0.x, -cv0.y}, c1v[2] = {-cv1.x, -cv1.y}; // accumulate -(A22) + P P^T, negate back on store
 #pragma unroll
 				for (int kk = 0; kk < FW / 4; kk++)
 				{
-					const double av = S[(r0 + g) * LP + c0 + kk * 4 + t];
-					const double bv = S[(q0 + g) * LP + c0 + kk * 4 + t];
-					gemm::dmma884(c, av, bv);
+					const double a0 = S[(r0 + g) * LP + c0 + kk * 4 + t], b0 = S[(q0 + g) * LP + c0 + kk * 4 + t];
+					const double a1 = S[(r1 + g) * LP + c0 + kk * 4 + t], b1 = S[(q1 + g) * LP + c0 + kk * 4 + t];
+					gemm::dmma884(c0v, a0, b0);
+					gemm::dmma884(c1v, a1, b1);
 				}
-				*cptr = make_double2(-c[0], -c[1]);
+				*cp0 = make_double2(-c0v[0], -c0v[1]);
+				if (second)
+				{
+					*cp1 = make_double2(-c1v[0], -c1v[1]);
+				}
 			}
 		}
 		__syncthreads();
