@@ -34,6 +34,14 @@ class ComplexScalars(C.Structure):
                 ("d_error", C.c_double * 8), ("d_purity", C.c_double * 8)]
 
 
+class McSource(C.Structure):
+    """gple_mc_source (include/gple_b200.h)"""
+    _fields_ = [("kind", C.c_int), ("row", C.c_int), ("col", C.c_int), ("analytic", C.c_double * 8), ("m00", C.c_void_p), ("m10", C.c_void_p),
+                ("m11", C.c_void_p), ("pes_model", C.c_int), ("mass", C.c_double), ("dt", C.c_double)]
+
+
+MC_ANALYTIC, MC_PREDICT, MC_NEW_POINT = 0, 1, 2
+
 # name -> (restype, argtypes); must list every symbol of include/gple_b200.h (tests/test_abi.py checks this)
 SIGNATURES = {
     "gple_version": (C.c_char_p, []),
@@ -50,6 +58,8 @@ SIGNATURES = {
     "gple_train_real": (C.c_int, [_vp, _dp, _dp, _sz, _dp, C.c_uint, C.POINTER(_vp), C.POINTER(RealScalars)]),
     "gple_train_complex": (C.c_int, [_vp, _dp, _dp, _sz, _dp, C.c_uint, C.POINTER(_vp), C.POINTER(ComplexScalars)]),
     "gple_model_get": (C.c_int, [_vp, _vp, C.c_int, _dp]),
+    "gple_markov_chains": (C.c_int, [_vp, C.POINTER(McSource), _dp, _sz, _sz, C.c_double, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, _dp, _dp]),
+    "gple_chain_autocorrelation": (C.c_int, [_vp, _dp, _sz, _sz, _dp]),
     "gple_model_nlml": (C.c_int, [_vp, _vp, _dp, _dp]),
     "gple_model_is_complex": (C.c_int, [_vp]),
     "gple_model_size": (_sz, [_vp]),

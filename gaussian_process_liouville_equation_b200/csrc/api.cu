@@ -2,6 +2,7 @@
 #include "chol.cuh"
 #include "evolve.cuh"
 #include "gpr.cuh"
+#include "mc.cuh"
 
 #include <exception>
 
@@ -649,6 +650,47 @@ extern "C"
 				DeviceArray<double> dr(ctx, r, 2 * n, false), o(ctx, out, 2 * n, true);
 				const gple_model* models[3] = {m00, m10, m11};
 				new_point_predict_device(ctx, pes_model, models, dr.dev, n, row, col, mass, dt, o.dev);
+				o.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_markov_chains(gple_ctx* ctx, const gple_mc_source* src, double* pts, size_t n, size_t num_steps, double max_displacement, unsigned long long seed, unsigned long long stream, unsigned long long chain0, double* accept_ratio, double* chains)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(src != nullptr && pts != nullptr && n > 0, "gple_markov_chains: null argument");
+				require(src->kind >= GPLE_MC_ANALYTIC && src->kind <= GPLE_MC_NEW_POINT, "gple_markov_chains: unknown source kind");
+				require(src->row >= 0 && src->row < 2 && src->col >= 0 && src->col <= src->row, "gple_markov_chains: (row, col) must be a lower-triangular index");
+				require(max_displacement > 0.0 && num_steps < 0xffffffffull, "gple_markov_chains: bad displacement or step count");
+				DeviceArray<double> p(ctx, pts, 4 * n, true), a(ctx, accept_ratio, n, true), c(ctx, chains, 2 * n * (num_steps + 1), true);
+				if (p.host != nullptr)
+				{
+					GPLE_CUDA(cudaMemcpyAsync(p.dev, p.host, 4 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+				}
+				markov_chains_device(ctx, *src, p.dev, n, num_steps, max_displacement, seed, stream, chain0, a.dev, c.dev);
+				p.finish();
+				a.finish();
+				c.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	int gple_chain_autocorrelation(gple_ctx* ctx, const double* chains, size_t n, size_t len, double* out)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(chains != nullptr && out != nullptr && n > 0 && len >= 2, "gple_chain_autocorrelation: null argument");
+				DeviceArray<double> c(ctx, chains, 2 * n * len, false), o(ctx, out, len / 2, true);
+				chain_autocorrelation_device(ctx, c.dev, n, len, o.dev);
 				o.finish();
 				sync(ctx);
 				return GPLE_OK;

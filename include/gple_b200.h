@@ -178,6 +178,37 @@ extern "C"
 	 *          sum (p^2/2m + E_pes(x)) Re rho, sum |rho|^2. */
 	int gple_observables(gple_ctx* ctx, int pes_model, const double* pts, size_t n, double mass, int pes_index, double out[9]);
 
+	/* ---- Metropolis sampling (gple/mc.cpp:125-403) ------------------------------------------------------
+	 * Replaces generate_markov_chain (mc.cpp:125-160) called once per point under par_unseq by element_monte_carlo
+	 * (:342-378), acceptance_optimize_displacement (:286-335) and autocorrelation_optimize_steps (:162-260): all n chains
+	 * of one element advance in lock-step, one batched density evaluation per step.  Target density
+	 * distribution(r, row, col) of the reference's DistributionFunction:
+	 *   GPLE_MC_ANALYTIC   initial_distribution (mc.cpp:30-50), analytic = {x0, p0, sigma_x, sigma_p, pop0, pop1, phase0, phase1}
+	 *   GPLE_MC_PREDICT    predict_distribution (main.cpp:75-101): cutoff prediction of the element's own model (0 if absent)
+	 *   GPLE_MC_NEW_POINT  new_point_predict (evolve.cpp:425-443) over the three models (pes_model, mass, dt)
+	 * The reference's shared clock-seeded mt19937 (mc.cpp:17) is replaced by one Philox4x32-10 stream per chain:
+	 * key = seed, counter = (chain0 + k, step, stream, block), so results do not depend on scheduling or sharding. */
+	enum gple_mc_kind
+	{
+		GPLE_MC_ANALYTIC = 0,
+		GPLE_MC_PREDICT = 1,
+		GPLE_MC_NEW_POINT = 2
+	};
+	typedef struct gple_mc_source
+	{
+		int kind;
+		int row, col; /* lower-triangular element index: (0,0), (1,0), (1,1) */
+		double analytic[8];
+		const gple_model *m00, *m10, *m11; /* NULL = element absent */
+		int pes_model;
+		double mass, dt;
+	} gple_mc_source;
+	/* pts: n x 4 (x, p, Re rho, Im rho), start points in, last state of every chain and its density out (mc.cpp:366-369).
+	 * accept_ratio: n doubles or NULL.  chains: n x (num_steps + 1) x 2 doubles (every state of every chain) or NULL. */
+	int gple_markov_chains(gple_ctx* ctx, const gple_mc_source* source, double* pts, size_t n, size_t num_steps, double max_displacement, unsigned long long seed, unsigned long long stream, unsigned long long chain0, double* accept_ratio, double* chains);
+	/* Mean autocorrelation of the chains (mc.cpp:187-203): out[j] = mean_k sum_i (r_i - <r>).(r_{i+j} - <r>) / (len - j), j < len / 2 */
+	int gple_chain_autocorrelation(gple_ctx* ctx, const double* chains, size_t n, size_t len, double* out);
+
 	/* ---- measurement helpers (bench.py) --------------------------------------------------------------- */
 	/* Per-kernel CUDA-event timing on the launching stream.  While enabled, every launch of the kernels below is
 	 * bracketed by an event pair; gple_profile_read synchronises, sums the elapsed times since the last read and

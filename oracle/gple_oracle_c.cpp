@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- C entry points of the CPU oracle for ctypes (tests/, smoke(), and the
 // cpu_baseline / --impl reference legs of bench.py).  The product library never links this file.
 #include "gple_oracle_dynamics.hpp"
+#include "gple_oracle_mc.hpp"
 #include "gple_oracle_nlml.hpp"
 
 #include <chrono>
@@ -441,5 +442,72 @@ extern "C"
 	double orc_nlml_complex(const void* h, double* grad)
 	{
 		return nlml_complex(*static_cast<const TrainingComplexKernel*>(h), grad);
+	}
+	// ---- Metropolis sampling (gple/mc.cpp:125-203) -------------------------------------------------------
+	/// kind 0: analytic initial distribution (analytic[8] as in orc_evolve); 1: predict_distribution of the models
+	/// (main.cpp:75-101); 2: new_point_predict over the models (evolve.cpp:425-443, needs model / mass / dt).
+	/// pts: n x 4 (x, p, re, im) in/out; accept: n doubles or NULL; chain_out: n x (num_steps + 1) x 2 or NULL.
+	void orc_markov_chains(int kind, const double* analytic, const void* h00, const void* h10, const void* h11, int model, double mass, double dt, int row, int col, double* pts, std::size_t n, std::size_t num_steps, double max_displacement, std::uint64_t seed, std::uint64_t stream, double* accept, double* chain_out)
+	{
+		Predictors pr;
+		pr.diag[0] = static_cast<const TrainingKernel*>(h00);
+		pr.diag[1] = static_cast<const TrainingKernel*>(h11);
+		pr.off = static_cast<const TrainingComplexKernel*>(h10);
+		const Distribution predict = make_distribution(pr);
+		Distribution dist = predict;
+		if (kind == 0)
+		{
+			const std::array<double, 2> r0{analytic[0], analytic[1]}, s0{analytic[2], analytic[3]}, pop{analytic[4], analytic[5]}, ph{analytic[6], analytic[7]};
+			dist = [=](const double x, const double p, const std::size_t r, const std::size_t c) -> cplx
+			{
+				return initial_distribution(r0, s0, x, p, r, c, pop, ph);
+			};
+		}
+		else if (kind == 2)
+		{
+			dist = [=](const double x, const double p, const std::size_t r, const std::size_t c) -> cplx
+			{
+				return new_point_predict(static_cast<Model>(model), x, p, mass, dt, predict, r, c);
+			};
+		}
+		parallel_for(
+			n,
+			[&](const std::size_t k)
+			{
+				double x = pts[4 * k], p = pts[4 * k + 1];
+				cplx rho;
+				const double a = markov_chain(dist, std::size_t(row), std::size_t(col), x, p, rho, num_steps, max_displacement, seed, stream, k, chain_out != nullptr ? chain_out + k * 2 * (num_steps + 1) : nullptr);
+				pts[4 * k] = x;
+				pts[4 * k + 1] = p;
+				pts[4 * k + 2] = rho.real();
+				pts[4 * k + 3] = rho.imag();
+				if (accept != nullptr)
+				{
+					accept[k] = a;
+				}
+			}
+		);
+	}
+	/// mean over the n chains of chain_autocorrelation: out[len / 2], chains laid out as orc_markov_chains writes them
+	void orc_chain_autocorrelation(const double* chains, std::size_t n, std::size_t len, double* out)
+	{
+		std::vector<double> one(len / 2);
+		std::fill(out, out + len / 2, 0.0);
+		for (std::size_t k = 0; k < n; k++)
+		{
+			chain_autocorrelation(chains + k * 2 * len, len, one.data());
+			for (std::size_t j = 0; j < len / 2; j++)
+			{
+				out[j] += one[j] / double(n);
+			}
+		}
+	}
+	/// the three uniforms of (seed, stream, chain, step): lets the tests pin the RNG itself
+	void orc_philox_draws(std::uint64_t seed, std::uint64_t stream, std::uint64_t chain, std::uint32_t step, double* out3)
+	{
+		const auto u = Philox::draws(seed, stream, chain, step);
+		out3[0] = u[0];
+		out3[1] = u[1];
+		out3[2] = u[2];
 	}
 }

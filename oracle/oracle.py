@@ -276,3 +276,33 @@ def initial_distribution(analytic, r, row, col):
     out = np.empty(len(r), dtype=np.complex128)
     lib().orc_initial_distribution(_p(analytic), _p(r), C.c_size_t(len(r)), int(row), int(col), out.ctypes.data_as(_dp))
     return out
+
+
+def markov_chains(pts, num_steps, max_displacement, seed, stream, row, col, analytic=None, k00=None, k10=None, k11=None, new_point=None, want_chain=False):
+    """gple/mc.cpp:125-160 for every point of pts (n, 4) at once, chain i on Philox stream (seed, stream, i).
+    Distribution: analytic[8] (initial_distribution), else predict_distribution of the models, else -- with
+    new_point = (model, mass, dt) -- new_point_predict.  Returns (pts_out (n, 4), accept (n,), chains (n, steps + 1, 2) | None)."""
+    pts = np.array(_f64(pts), copy=True)
+    n = len(pts)
+    kind = 0 if analytic is not None else (2 if new_point is not None else 1)
+    model, mass, dt = new_point if new_point is not None else (0, 1.0, 0.0)
+    accept = np.empty(n)
+    chains = np.empty((n, num_steps + 1, 2)) if want_chain else None
+    lib().orc_markov_chains(kind, _p(None if analytic is None else _f64(analytic)), _h(k00), _h(k10), _h(k11), int(model), C.c_double(mass), C.c_double(dt), int(row), int(col), _p(pts),
+                            C.c_size_t(n), C.c_size_t(num_steps), C.c_double(max_displacement), C.c_uint64(seed), C.c_uint64(stream), _p(accept), _p(chains))
+    return pts, accept, chains
+
+
+def chain_autocorrelation(chains):
+    """gple/mc.cpp:187-203: mean autocorrelation over the chains, chains (n, len, 2) -> (len // 2,)"""
+    chains = _f64(chains)
+    n, length = chains.shape[0], chains.shape[1]
+    out = np.empty(length // 2)
+    lib().orc_chain_autocorrelation(_p(chains), C.c_size_t(n), C.c_size_t(length), _p(out))
+    return out
+
+
+def philox_draws(seed, stream, chain, step):
+    out = np.empty(3)
+    lib().orc_philox_draws(C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(chain), C.c_uint32(step), _p(out))
+    return out

@@ -61,3 +61,33 @@ def loose_function(x, TrainingSet, ExtraTrainingSet, grad=False):
 
 def observable_sums(model, pts, mass, pes_index):
     return orc.observable_sums(model, np.asarray(pts), mass, pes_index)
+
+
+class Sampler:
+    """Oracle twin of gaussian_process_liouville_equation_b200.mc.Sampler (same Philox streams, same call counter)."""
+
+    def __init__(self, seed, analytic=None, kernels=None, new_point=None):
+        self.seed, self.calls = int(seed), 0
+        self.analytic, self.kernels, self.new_point = analytic, kernels, new_point
+
+    def next_stream(self, element):
+        self.calls += 1
+        return self.calls * 4 + element
+
+    def chains(self, pts, num_steps, max_displacement, row, col, want_chain=False, stream=None):
+        stream = self.next_stream(row + col) if stream is None else stream
+        analytic = None
+        if self.analytic is not None:
+            r0, s0, pop, ph = self.analytic
+            analytic = [r0[0], r0[1], s0[0], s0[1], pop[0], pop[1], ph[0], ph[1]]
+        k = [None, None, None] if self.kernels is None else [getattr(x, "o", x) for x in self.kernels]
+        return orc.markov_chains(pts, num_steps, max_displacement, self.seed, stream, row, col, analytic=analytic, k00=k[0], k10=k[1], k11=k[2], new_point=self.new_point, want_chain=want_chain)
+
+    def autocorrelation(self, chains):
+        return orc.chain_autocorrelation(chains)
+
+    def density(self, r, row, col):
+        pts = np.zeros((len(r), 4))
+        pts[:, :2] = r
+        out, _, _ = self.chains(pts, 0, 1.0, row, col, stream=0)
+        return out[:, 2] + 1j * out[:, 3]
