@@ -160,7 +160,7 @@ public:
 
 	TrainingKernel(const ParameterVector& Parameter, const ElementTrainingSet& TrainingSet, bool IsToCalculateError, bool IsToCalculateAverage, bool IsToCalculateDerivative):
 		Params(Parameter), Feature(std::get<0>(TrainingSet)), N(std::get<0>(TrainingSet).cols()),
-		Flags((IsToCalculateError ? GPLE_CALC_ERROR : 0u) | (IsToCalculateAverage ? GPLE_CALC_AVERAGE : 0u) | (IsToCalculateDerivative ? GPLE_CALC_DERIVATIVE : 0u))
+		Flags((IsToCalculateError ? unsigned(GPLE_CALC_ERROR) : 0u) | (IsToCalculateAverage ? unsigned(GPLE_CALC_AVERAGE) : 0u) | (IsToCalculateDerivative ? unsigned(GPLE_CALC_DERIVATIVE) : 0u))
 	{
 		assert(Parameter.size() == NumTotalParameters);
 		gple_model* m = nullptr;
@@ -244,7 +244,7 @@ public:
 	using ParameterArray = std::array<T, NumTotalParameters>;
 	TrainingComplexKernel(const ParameterVector& Parameter, const ElementTrainingSet& TrainingSet, bool IsToCalculateError, bool IsToCalculateAverage, bool IsToCalculateDerivative):
 		Params(Parameter), N(std::get<0>(TrainingSet).cols()),
-		Flags((IsToCalculateError ? GPLE_CALC_ERROR : 0u) | (IsToCalculateAverage ? GPLE_CALC_AVERAGE : 0u) | (IsToCalculateDerivative ? GPLE_CALC_DERIVATIVE : 0u))
+		Flags((IsToCalculateError ? unsigned(GPLE_CALC_ERROR) : 0u) | (IsToCalculateAverage ? unsigned(GPLE_CALC_AVERAGE) : 0u) | (IsToCalculateDerivative ? unsigned(GPLE_CALC_DERIVATIVE) : 0u))
 	{
 		assert(Parameter.size() == NumTotalParameters);
 		gple_model* m = nullptr;

@@ -89,3 +89,23 @@ def test_large_walk_keeps_the_target_distribution():
     assert abs(out[:, 0].mean() - syn.X0) < se * syn.SIGMA_X and abs(out[:, 1].mean() - syn.P0) < se * syn.SIGMA_P
     assert out[:, 0].std() == pytest.approx(syn.SIGMA_X, rel=0.01) and out[:, 1].std() == pytest.approx(syn.SIGMA_P, rel=0.01)
     assert 0.3 < acc.mean() < 0.9
+
+
+def test_cpp_host_monte_carlo_selection_matches_oracle_sampler(tmp_path):
+    """host/gple_mc.hpp drives the same walks as mc.py: identical tuned parameters and points as the oracle-backed run."""
+    import subprocess
+
+    from test_opt_cpp import compile_cpp
+
+    exe = compile_cpp("mc_test", link=True)
+    pts = start_points(89, 40, (syn.X0, syn.P0))
+    path = tmp_path / "start.txt"
+    path.write_text(f"{len(pts)}\n" + "".join(f"{float(x)!r} {float(p)!r}\n" for x, p in pts[:, :2]))
+    out = subprocess.run([exe, str(path), "21"], capture_output=True, text=True, check=True).stdout
+    got = {k: float(v) for k, v in (line.split() for line in out.strip().splitlines())}
+    params = [mc.MCParameters() for _ in range(3)]
+    ref = mc.monte_carlo_selection([pts, pts.copy(), None], params, oracle_backend.Sampler(21, analytic=ANALYTIC))
+    for e in range(2):
+        assert got[f"displacement{e}"] == params[e].get_max_displacement() and got[f"steps{e}"] == params[e].get_num_MC_steps()
+        walked = np.array([[got[f"p{e}_{i}_{c}"] for c in ("x", "p", "re", "im")] for i in range(len(pts))])
+        assert np.abs(walked - ref[e]).max() <= 1e-12 * np.abs(ref[e]).max()

@@ -37,6 +37,10 @@ def test_optimiser_mirror_compiles_and_links():
     assert os.path.exists(compile_cpp("opt_test", link=True))
 
 
+def test_metropolis_mirror_compiles_and_links():
+    assert os.path.exists(compile_cpp("mc_test", link=True))
+
+
 def write_points(path, density, extra):
     with open(path, "w") as f:
         for group in (density, extra):
