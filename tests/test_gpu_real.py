@@ -209,3 +209,21 @@ def test_nlml_objective_parity(gk, oracle):
     assert v == pytest.approx(ov, rel=1e-9)
     assert np.abs(g - og).max() <= 1e-7 * np.abs(og).max()
     assert k.get_negative_log_marginal_likelihood() == v
+
+
+@pytest.mark.parametrize("n", [1100, 1664, 2100, 4200])
+def test_factorisation_schedules_on_ragged_block_counts(gk, n):
+    """9, 13, 17 and 33 blocks of 128: odd block counts exercise the ragged pairs of the level-batched triangular inverse,
+    n = 4200 the switch from the recursive form (above 4096 rows) to the right-looking sweep inside it."""
+    X, y = syn.training_set(5, 0, n)
+    th = syn.theta_real((2048.0 / max(n, 2048)) ** 0.5)
+    k = gk.TrainingKernel(th, (X, y), True, False, False)
+    assert k.status == 0
+    K = gk.kernel_matrix(X, X, th, True)
+    v, lab = k.get_inverse_times_label(), k.get_label()
+    assert np.abs(K @ v - lab).max() <= 1e-8 * np.abs(lab).max()
+    Kinv = k.get_inverse()
+    assert np.abs(Kinv - Kinv.T).max() <= 1e-9 * np.abs(Kinv).max()
+    probe = np.random.default_rng(n).standard_normal((n, 8))
+    assert np.abs(K @ (Kinv @ probe) - probe).max() <= 1e-7 * np.abs(probe).max()
+    assert k.get_error() == pytest.approx(float(np.sum((v / np.diag(Kinv)) ** 2)), rel=1e-9)
