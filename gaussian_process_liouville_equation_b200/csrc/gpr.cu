@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 		const GaussBlock g = spec.b[rb][cb];
 		const double* __restrict__ wb = w + cb * Np;
 		double* __restrict__ ob = out + cb * Np;
+#pragma unroll 4
 		for (int j = lane * 2; j < Np; j += 64)
 		{
 			double2 val = make_double2(0.0, 0.0);
