@@ -281,10 +281,10 @@ def run_ours(args):
     ctx.profile_enable(False)
     clocks = sampler.stop()
 
-    rows_total = rows_var = rows_zero = 0
+    rows_total = rows_var = rows_zero = rows_b = 0
     for c in train_ctx:
-        a_, b_, c_ = c.gate_statistics()
-        rows_total, rows_var, rows_zero = rows_total + a_, rows_var + b_, rows_zero + c_
+        a_, b_, c_, d_ = c.gate_statistics()
+        rows_total, rows_var, rows_zero, rows_b = rows_total + a_, rows_var + b_, rows_zero + c_, rows_b + d_
     # the same step with every variance computed (GPLE_OPT_GATED_VARIANCE = 0), for comparison
     ctx.set_gated_variance(False)
     reset()
@@ -327,9 +327,9 @@ def run_ours(args):
                   "dmma_register_tile_ceiling_note": "same 8x4 DMMA register tile at 8 warps/SM with changing operands and no memory traffic: the ceiling of an mma.sync FP64 GEMM at this occupancy",
                   "kernel_build_gbs": kb_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else None, "kernel_build_share": kb_ms / total_ms,
                   "cholesky_inverse_tflops": fa_flops / (fa_ms * 1e-3) / 1e12 if fa_ms > 0 else None, "factorise_share": fa_ms / total_ms,
-                  "gated_variance": {"enabled": True, "rows_total": rows_total, "rows_through_variance_gemm": rows_var, "rows_decided_zero": rows_zero,
-                                     "fraction": rows_var / max(rows_total, 1),
-                                     "note": "cutoff gate == 1 exactly when |f|^2 >= 4 k** (computed variance never exceeds the prior k**), == 0 exactly when |f|^2 <= noise/2 (variance >= noise): those queries skip the variance GEMM; outputs agree to rounding (tests/test_gpu_dynamics.py)"},
+                  "gated_variance": {"enabled": True, "rows_total": rows_total, "rows_through_variance_gemm": rows_var, "rows_decided_zero": rows_zero, "rows_needing_the_full_variance": rows_b,
+                                     "fraction": rows_var / max(rows_total, 1), "fraction_full": rows_b / max(rows_total, 1),
+                                     "note": "exact short-cuts of the cutoff gate (kernel.h:301-332): gate == 1 when |f|^2 >= 4 k** (variance <= prior) or when |f|^2 >= 4 (k** - sum Z^2 over the columns of the first 4 training blocks) (variance <= variance given those points only); gate == 0 when |f|^2 <= noise/2 (variance >= noise); only the undecided queries get the full variance; outputs agree to rounding with the full computation (tests/test_gpu_dynamics.py), whose rate is reported next to it"},
                   "value_with_every_variance_computed": 1000.0 / (full_ms / args.steps), "ms_per_step_with_every_variance_computed": full_ms / args.steps,
                   "reference_formulation_tflops_equiv": alg_flops_step / ((full_ms / args.steps) * 1e-3) / 1e12,
                   "check": last_scalars},

@@ -145,10 +145,13 @@ class Context:
     def set_gated_variance(self, on: bool):
         self.check(self.lib.gple_ctx_set_option(self.h, 1, int(on)))
 
+    def set_gate_stage_tiles(self, tiles: int):
+        self.check(self.lib.gple_ctx_set_option(self.h, 2, int(tiles)))
+
     def gate_statistics(self):
-        out = (C.c_ulonglong * 3)()
+        out = (C.c_ulonglong * 4)()
         self.check(self.lib.gple_gate_statistics(self.h, out))
-        return int(out[0]), int(out[1]), int(out[2])
+        return int(out[0]), int(out[1]), int(out[2]), int(out[3])
 
     def sync(self):
         self.check(self.lib.gple_ctx_sync(self.h))

@@ -252,15 +252,24 @@ extern "C"
 
 	int gple_ctx_set_option(gple_ctx* ctx, int option, int value)
 	{
-		if (ctx == nullptr || option != GPLE_OPT_GATED_VARIANCE)
+		if (ctx == nullptr)
 		{
 			return GPLE_ERR_ARG;
 		}
-		ctx->gated_variance = value != 0;
-		return GPLE_OK;
+		if (option == GPLE_OPT_GATED_VARIANCE)
+		{
+			ctx->gated_variance = value != 0;
+			return GPLE_OK;
+		}
+		if (option == GPLE_OPT_GATE_STAGE_TILES && value >= 0)
+		{
+			ctx->gate_stage_tiles = value;
+			return GPLE_OK;
+		}
+		return GPLE_ERR_ARG;
 	}
 
-	int gple_gate_statistics(gple_ctx* ctx, unsigned long long out[3])
+	int gple_gate_statistics(gple_ctx* ctx, unsigned long long out[4])
 	{
 		if (ctx == nullptr || out == nullptr)
 		{
@@ -269,7 +278,8 @@ extern "C"
 		out[0] = ctx->gate_rows_total;
 		out[1] = ctx->gate_rows_variance;
 		out[2] = ctx->gate_rows_zero;
-		ctx->gate_rows_total = ctx->gate_rows_variance = ctx->gate_rows_zero = 0;
+		out[3] = ctx->gate_rows_stage_b;
+		ctx->gate_rows_total = ctx->gate_rows_variance = ctx->gate_rows_zero = ctx->gate_rows_stage_b = 0;
 		return GPLE_OK;
 	}
 

@@ -306,8 +306,27 @@ void launch_kmean(gple_ctx* ctx, const BlockSpec& spec, const double2* Xq, long 
 /// One CTA owns 128 query rows and walks all n-tiles; the cp.async pipeline runs across n-tile boundaries
 /// (flattened (n-tile, k-step) sequence) so the tensor pipe never drains.  The squared accumulators are
 /// folded into per-thread row sums; no Z is ever written.
+/// The n-tiles a launch walks: two runs of consecutive 128-wide tiles, [b0, b0 + c0) then [b1, b1 + c1).  Any subset of the
+/// columns of Z gives a LOWER bound of sum Z^2, i.e. an upper bound of the variance -- the staged gate uses that.
+struct TileSet
+{
+	int b0, c0, b1, c1;
+	__host__ __device__ int count() const { return c0 + c1; }
+	__host__ __device__ int tile(const int v) const { return v < c0 ? b0 + v : b1 + (v - c0); }
+	/// sum over the set of (tile + 1): the k-length of the triangular products in units of 128
+	double weight() const
+	{
+		double w = 0.0;
+		for (int v = 0; v < count(); v++)
+		{
+			w += double(tile(v) + 1);
+		}
+		return w;
+	}
+};
+
 template <typename C>
-__global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* __restrict__ A, const double* __restrict__ W, const int n, double* __restrict__ q, const int rows)
+__global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* __restrict__ A, const double* __restrict__ W, const int n, double* __restrict__ q, const int rows, const TileSet ts)
 {
 	using namespace gemm;
 	extern __shared__ __align__(16) double smem[];
@@ -318,16 +337,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 	constexpr int BM = 128, BN = 128;
 	static_assert(C::BM == 128 && C::BN == 128, "the variance GEMM walks 128-wide n-tiles");
 	const int m0 = blockIdx.x * BM;
-	const int T = n / BN;
+	const int V = ts.count();
 	const double* Ag = A + size_t(m0) * n;
 	// When a chunk has fewer than ~148 row blocks the n-tiles are dealt round-robin to gridDim.y CTAs per row
 	// block (interleaving balances the triangular work); each writes its partial row sums to q[blockIdx.y][rows].
 	const int nt0 = blockIdx.y, nts = gridDim.y;
 
-	int l_nt = nt0, l_kt = 0, l_slot = 0;
+	int l_v = nt0, l_nt = ts.tile(nt0), l_kt = 0, l_slot = 0;
 	auto issue = [&]()
 	{
-		if (l_nt < T)
+		if (l_v < V)
 		{
 			load_tile_kmajor<C, 128>(As + l_slot * C::A_STAGE, Ag + size_t(l_kt) * C::BK, size_t(n), tid);
 			load_tile_kmajor<C, 128>(Bs + l_slot * C::B_STAGE, W + size_t(l_nt) * BN * n + size_t(l_kt) * C::BK, size_t(n), tid);
@@ -335,7 +354,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 			if (++l_kt == (l_nt + 1) * (BN / C::BK))
 			{
 				l_kt = 0;
-				l_nt += nts;
+				l_v += nts;
+				l_nt = ts.tile(l_v);
 			}
 		}
 		cp_async_commit();
@@ -353,10 +373,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 	}
 	double acc[C::MI][C::NJ][2];
 	int c_slot = 0;
-	for (int nt = nt0; nt < T; nt += nts)
+	for (int v = nt0; v < V; v += nts)
 	{
 		zero_acc<C>(acc);
-		const int steps = (nt + 1) * (BN / C::BK);
+		const int steps = (ts.tile(v) + 1) * (BN / C::BK);
 		for (int kt = 0; kt < steps; kt++)
 		{
 			cp_async_wait<C::STAGES - 2>();
@@ -433,7 +453,7 @@ constexpr int MAX_VAR_SPLITS = 16;
 int g_var_variant = 1; // BK = 32, 3 stages, 2 x 4 warps: 88.8 % of the DMMA peak on B200 (profiles/r01_tune_var_gemm.txt)
 
 template <typename C>
-void launch_var_gemm_cfg(gple_ctx* ctx, const double* A, const double* W, int n, int rows, double* q)
+void launch_var_gemm_cfg(gple_ctx* ctx, const double* A, const double* W, int n, int rows, double* q, const TileSet& ts)
 {
 	static bool attr_done = false;
 	if (!attr_done)
@@ -442,7 +462,7 @@ void launch_var_gemm_cfg(gple_ctx* ctx, const double* A, const double* W, int n,
 		attr_done = true;
 	}
 	// choose the number of n-splits S that minimises the makespan ceil(blocks * S / SMs) / S
-	const int mb = rows / 128, T = n / 128;
+	const int mb = rows / 128, T = ts.count();
 	int best = 1;
 	double best_cost = double((mb + ctx->num_sms - 1) / ctx->num_sms);
 	for (int S = 2; S <= std::min(T, MAX_VAR_SPLITS); S++)
@@ -454,31 +474,37 @@ void launch_var_gemm_cfg(gple_ctx* ctx, const double* A, const double* W, int n,
 			best = S;
 		}
 	}
-	GPLE_LAUNCH(ctx, var_gemm_kernel<C>, dim3(mb, best), C::THREADS, C::SMEM_BYTES, A, W, n, q, rows);
+	GPLE_LAUNCH(ctx, var_gemm_kernel<C>, dim3(mb, best), C::THREADS, C::SMEM_BYTES, A, W, n, q, rows, ts);
 	if (best > 1)
 	{
 		GPLE_LAUNCH(ctx, var_reduce_kernel, (rows + 255) / 256, 256, 0, q, rows, best);
 	}
 }
 
-void launch_var_gemm(gple_ctx* ctx, int variant, const double* A, const double* W, int n, int rows, double* q)
+/// flops executed by a launch over `rows` rows: 2 * 128^2 * sum over the tile set of (tile + 1) per row
+double var_gemm_flops(const TileSet& ts, int rows)
+{
+	return 2.0 * 128.0 * 128.0 * ts.weight() * double(rows);
+}
+
+void launch_var_gemm(gple_ctx* ctx, int variant, const double* A, const double* W, int n, int rows, double* q, const TileSet& ts)
 {
 	switch (variant)
 	{
 	case 1:
-		return launch_var_gemm_cfg<VarCfg1>(ctx, A, W, n, rows, q);
+		return launch_var_gemm_cfg<VarCfg1>(ctx, A, W, n, rows, q, ts);
 	case 2:
-		return launch_var_gemm_cfg<VarCfg2>(ctx, A, W, n, rows, q);
+		return launch_var_gemm_cfg<VarCfg2>(ctx, A, W, n, rows, q, ts);
 	case 3:
-		return launch_var_gemm_cfg<VarCfg3>(ctx, A, W, n, rows, q);
+		return launch_var_gemm_cfg<VarCfg3>(ctx, A, W, n, rows, q, ts);
 	case 4:
-		return launch_var_gemm_cfg<VarCfg4>(ctx, A, W, n, rows, q);
+		return launch_var_gemm_cfg<VarCfg4>(ctx, A, W, n, rows, q, ts);
 	case 5:
-		return launch_var_gemm_cfg<VarCfg5>(ctx, A, W, n, rows, q);
+		return launch_var_gemm_cfg<VarCfg5>(ctx, A, W, n, rows, q, ts);
 	case 6:
-		return launch_var_gemm_cfg<VarCfg6>(ctx, A, W, n, rows, q);
+		return launch_var_gemm_cfg<VarCfg6>(ctx, A, W, n, rows, q, ts);
 	default:
-		return launch_var_gemm_cfg<VarCfg0>(ctx, A, W, n, rows, q);
+		return launch_var_gemm_cfg<VarCfg0>(ctx, A, W, n, rows, q, ts);
 	}
 }
 
@@ -537,6 +563,46 @@ __global__ void __launch_bounds__(256) classify_kernel(const double* __restrict_
 }
 
 /// kernel.cpp:496-519 + kernel.h:301-332: variance, cubic gate, cutoff prediction (real element)
+/// Second stage of the gate: q1 = sum Z^2 over the stage-A tile set gives var <= k** - q1, so |f|^2 >= 4 (k** - q1) decides
+/// gate == 1 exactly.  One thread per listed query (nb consecutive list entries).  slot2[entry] = -1 (decided) or the
+/// entry's position in the stage-B list idx2 (original composite rows).  counter[2] = stage-B rows.
+__global__ void __launch_bounds__(256) classify2_kernel(const double* __restrict__ pred, const int* __restrict__ idx1, const double* __restrict__ q1, const int queries, const int nb, const double prior, int* __restrict__ idx2, int* __restrict__ slot2, int* __restrict__ counter)
+{
+	const int e = blockIdx.x * 256 + threadIdx.x;
+	bool need = false;
+	if (e < queries)
+	{
+		double f2 = 0.0, qs = 0.0;
+		for (int k = 0; k < nb; k++)
+		{
+			const double f = pred[idx1[e * nb + k]];
+			f2 = fma(f, f, f2);
+			qs += q1[e * nb + k];
+		}
+		need = !(f2 >= 4.0 * (prior - qs)); // NaN keeps the full path
+	}
+	const unsigned ballot = __ballot_sync(0xffffffffu, need);
+	const int lane = threadIdx.x & 31;
+	int base = 0;
+	if (lane == 0 && ballot != 0u)
+	{
+		base = atomicAdd(counter + 2, __popc(ballot) * nb);
+	}
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (e < queries)
+	{
+		const int mine = base + __popc(ballot & ((1u << lane) - 1u)) * nb;
+		for (int k = 0; k < nb; k++)
+		{
+			slot2[e * nb + k] = need ? mine + k : -1;
+			if (need)
+			{
+				idx2[mine + k] = idx1[e * nb + k];
+			}
+		}
+	}
+}
+
 __device__ __forceinline__ double gate_factor(const double pred_sq, const double abs_pred, const double var)
 {
 	if (pred_sq >= 4.0 * var) // ConnectingPoint^2 (also taken for var < 0: quirk q5)
@@ -551,7 +617,7 @@ __device__ __forceinline__ double gate_factor(const double pred_sq, const double
 	return (5.0 - 2.0 * a) * (a - 1.0) * (a - 1.0);
 }
 
-__global__ void finalize_real_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double* __restrict__ pred_out, double* __restrict__ var_out, double* __restrict__ cut_out)
+__global__ void finalize_real_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int* __restrict__ slot2, const double* __restrict__ q2, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double* __restrict__ pred_out, double* __restrict__ var_out, double* __restrict__ cut_out)
 {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= rows || row0 + r >= Q)
@@ -560,8 +626,10 @@ __global__ void finalize_real_kernel(const double* __restrict__ pred, const doub
 	}
 	const double f = pred[r];
 	const int sl = slot != nullptr ? slot[r] : r;
-	const double var = sl >= 0 ? prior - q[sl] : prior; // sl < 0: gate decided by a bound (classify_kernel), variance not computed
-	const double gate = sl >= 0 ? gate_factor(f * f, fabs(f), var) : (sl == -1 ? 1.0 : 0.0);
+	// sl < 0: gate decided by a bound (classify_kernel); s2 == -1: decided 1 by the stage-A bound (classify2_kernel)
+	const int s2 = (sl >= 0 && slot2 != nullptr) ? slot2[sl] : 0;
+	const double var = sl >= 0 ? prior - q[sl] - ((slot2 != nullptr && s2 >= 0) ? q2[s2] : 0.0) : prior;
+	const double gate = sl >= 0 ? (s2 == -1 ? 1.0 : gate_factor(f * f, fabs(f), var)) : (sl == -1 ? 1.0 : 0.0);
 	if (pred_out != nullptr)
 	{
 		pred_out[row0 + r] = f;
@@ -577,7 +645,7 @@ __global__ void finalize_real_kernel(const double* __restrict__ pred, const doub
 }
 
 /// complex_kernel.cpp:608-643 in composite form: rows (2m, 2m+1) = (Re, Im) parts of query m
-__global__ void finalize_complex_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double2* __restrict__ pred_out, double* __restrict__ var_out, double2* __restrict__ cut_out)
+__global__ void finalize_complex_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int* __restrict__ slot2, const double* __restrict__ q2, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double2* __restrict__ pred_out, double* __restrict__ var_out, double2* __restrict__ cut_out)
 {
 	const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
 	const long long m = row0 / 2 + pidx;
@@ -587,9 +655,10 @@ __global__ void finalize_complex_kernel(const double* __restrict__ pred, const d
 	}
 	const double fr = pred[2 * pidx], fi = pred[2 * pidx + 1];
 	const int sl = slot != nullptr ? slot[2 * pidx] : 2 * pidx;
-	const double var = sl >= 0 ? prior - q[sl] - q[sl + 1] : prior;
+	const int s2 = (sl >= 0 && slot2 != nullptr) ? slot2[sl] : 0;
+	const double var = sl >= 0 ? prior - q[sl] - q[sl + 1] - ((slot2 != nullptr && s2 >= 0) ? q2[s2] + q2[s2 + 1] : 0.0) : prior;
 	const double ps = fr * fr + fi * fi;
-	const double gate = sl >= 0 ? gate_factor(ps, hypot(fr, fi), var) : (sl == -1 ? 1.0 : 0.0);
+	const double gate = sl >= 0 ? (s2 == -1 ? 1.0 : gate_factor(ps, hypot(fr, fi), var)) : (sl == -1 ? 1.0 : 0.0);
 	if (pred_out != nullptr)
 	{
 		pred_out[m] = make_double2(fr, fi);
@@ -1302,25 +1371,59 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		ctx->gate_rows_total += (unsigned long long)total_rows;
 		ctx->gate_rows_variance += (unsigned long long)count;
 		ctx->gate_rows_zero += (unsigned long long)counts[1];
+		// ---- stage A: the listed rows against a small tile set (the first `stage` 128-blocks of training points: for the
+		// complex element the Re rows of those points plus their Im rows, which sit after all Re rows in the composite order).
+		// k** - sum Z^2 over a subset of Z's columns is the posterior variance given only those observations: an upper bound
+		// of the variance that is already close to the noise floor inside the point cloud.
+		const int T = n / 128, Th = m->is_complex ? T / 2 : T;
+		const int stage = std::min(ctx->gate_stage_tiles, Th);
+		const bool staged = stage > 0 && stage < Th && count > 0;
+		const TileSet full{0, T, 0, 0};
+		const TileSet setA = !staged ? full : (m->is_complex ? TileSet{0, stage, Th, stage} : TileSet{0, stage, 0, 0});
+		const TileSet setB = m->is_complex ? TileSet{stage, Th - stage, Th + stage, Th - stage} : TileSet{stage, T - stage, 0, 0};
 		double* q = ctx->ws.get<double>("pred.q_all", round_up(size_t(count), 128) + size_t(CHUNK_ROWS) * MAX_VAR_SPLITS);
-		for (long long c0 = 0; c0 < count; c0 += CHUNK_ROWS)
+		auto sweep = [&](const int* list, const int list_count, const TileSet& ts, double* qout)
 		{
-			const int rows_real = int(std::min<long long>(CHUNK_ROWS, count - c0));
-			const int rows = int(round_up(size_t(rows_real), 128));
+			for (long long c0 = 0; c0 < list_count; c0 += CHUNK_ROWS)
 			{
-				ProfScope prof(ctx, GPLE_PROF_KERNEL_BUILD, 8.0 * double(rows) * n, 1);
-				GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, c0, rows, gate_idx, (long long)count, Xt2, int(m->N), m->Np, n, m->v, A, nullptr);
+				const int rows_real = int(std::min<long long>(CHUNK_ROWS, list_count - c0));
+				const int rows = int(round_up(size_t(rows_real), 128));
+				{
+					ProfScope prof(ctx, GPLE_PROF_KERNEL_BUILD, 8.0 * double(rows) * n, 1);
+					GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, c0, rows, list, (long long)list_count, Xt2, int(m->N), m->Np, n, m->v, A, nullptr);
+				}
+				ProfScope prof(ctx, GPLE_PROF_VARIANCE_GEMM, var_gemm_flops(ts, rows), 1);
+				launch_var_gemm(ctx, g_var_variant, A, m->W, n, rows, qout + c0, ts);
 			}
-			ProfScope prof(ctx, GPLE_PROF_VARIANCE_GEMM, double(rows) * n * (double(n) + 128.0), 1);
-			launch_var_gemm(ctx, g_var_variant, A, m->W, n, rows, q + c0);
-		}
-		if (m->is_complex)
+		};
+		sweep(gate_idx, count, setA, q);
+		int* slot2 = nullptr;
+		double* q2 = nullptr;
+		if (staged)
 		{
-			GPLE_LAUNCH(ctx, finalize_complex_kernel, unsigned((total_rows / 2 + 255) / 256), 256, 0, pred, q, gate_slot, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
+			// ---- stage B: only the queries the stage-A bound does not decide see the remaining tiles
+			int* idx2 = ctx->ws.get<int>("pred.gate_idx2", round_up(size_t(count), 128));
+			slot2 = ctx->ws.get<int>("pred.gate_slot2", round_up(size_t(count), 128));
+			GPLE_LAUNCH(ctx, classify2_kernel, unsigned((count / nb + 255) / 256), 256, 0, pred, gate_idx, q, count / nb, nb, m->prior, idx2, slot2, gate_cnt);
+			GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 204, gate_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+			GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
+			int count2 = 0;
+			std::memcpy(&count2, ctx->h_pinned + 204, sizeof(int));
+			ctx->gate_rows_stage_b += (unsigned long long)count2;
+			q2 = ctx->ws.get<double>("pred.q2_all", round_up(size_t(count2), 128) + size_t(CHUNK_ROWS) * MAX_VAR_SPLITS);
+			sweep(idx2, count2, setB, q2);
 		}
 		else
 		{
-			GPLE_LAUNCH(ctx, finalize_real_kernel, unsigned((total_rows + 255) / 256), 256, 0, pred, q, gate_slot, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
+			ctx->gate_rows_stage_b += (unsigned long long)count;
+		}
+		if (m->is_complex)
+		{
+			GPLE_LAUNCH(ctx, finalize_complex_kernel, unsigned((total_rows / 2 + 255) / 256), 256, 0, pred, q, gate_slot, slot2, q2, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
+		}
+		else
+		{
+			GPLE_LAUNCH(ctx, finalize_real_kernel, unsigned((total_rows + 255) / 256), 256, 0, pred, q, gate_slot, slot2, q2, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
 		}
 		if (d_err != nullptr && d_yq != nullptr)
 		{
@@ -1345,7 +1448,7 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 				GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, row0, rows, nullptr, 0ll, Xt2, int(m->N), m->Np, n, m->v, A, pred);
 			}
 			ProfScope prof(ctx, GPLE_PROF_VARIANCE_GEMM, double(rows) * n * (double(n) + 128.0), 1);
-			launch_var_gemm(ctx, g_var_variant, A, m->W, n, rows, q);
+			launch_var_gemm(ctx, g_var_variant, A, m->W, n, rows, q, TileSet{0, n / 128, 0, 0});
 		}
 		else
 		{
@@ -1356,11 +1459,11 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		}
 		if (m->is_complex)
 		{
-			GPLE_LAUNCH(ctx, finalize_complex_kernel, (rows / 2 + 255) / 256, 256, 0, pred, q, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
+			GPLE_LAUNCH(ctx, finalize_complex_kernel, (rows / 2 + 255) / 256, 256, 0, pred, q, nullptr, nullptr, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
 		}
 		else
 		{
-			GPLE_LAUNCH(ctx, finalize_real_kernel, (rows + 255) / 256, 256, 0, pred, q, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
+			GPLE_LAUNCH(ctx, finalize_real_kernel, (rows + 255) / 256, 256, 0, pred, q, nullptr, nullptr, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
 		}
 		if (d_err != nullptr && d_yq != nullptr)
 		{
@@ -1388,14 +1491,14 @@ double bench_variance_gemm(gple_ctx* ctx, int variant, int rows, int n, int iter
 	double* q = ctx->ws.get<double>("pred.q", size_t(rows) * MAX_VAR_SPLITS);
 	GPLE_CUDA(cudaMemsetAsync(A, 0, size_t(rows) * n * sizeof(double), ctx->stream));
 	GPLE_CUDA(cudaMemsetAsync(W, 0, size_t(n) * n * sizeof(double), ctx->stream));
-	launch_var_gemm(ctx, variant, A, W, n, rows, q);
+	launch_var_gemm(ctx, variant, A, W, n, rows, q, TileSet{0, n / 128, 0, 0});
 	cudaEvent_t e0, e1;
 	GPLE_CUDA(cudaEventCreate(&e0));
 	GPLE_CUDA(cudaEventCreate(&e1));
 	GPLE_CUDA(cudaEventRecord(e0, ctx->stream));
 	for (int i = 0; i < iters; i++)
 	{
-		launch_var_gemm(ctx, variant, A, W, n, rows, q);
+		launch_var_gemm(ctx, variant, A, W, n, rows, q, TileSet{0, n / 128, 0, 0});
 	}
 	GPLE_CUDA(cudaEventRecord(e1, ctx->stream));
 	GPLE_CUDA(cudaEventSynchronize(e1));

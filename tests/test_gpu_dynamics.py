@@ -86,13 +86,15 @@ def test_observables_parity(dyn, oracle):
 
 
 def test_bound_gated_variance_changes_nothing(dyn):
-    """GPLE_OPT_GATED_VARIANCE only skips variances whose gate is decided by var <= k**: coordinates are bit-identical
-    and densities agree to rounding with the option on and off (the rows that still go through the variance GEMM may
-    use a different n-split, i.e. a different summation order of the same terms); rows must have been skipped."""
+    """GPLE_OPT_GATED_VARIANCE / GPLE_OPT_GATE_STAGE_TILES only skip variances whose gate is decided by a bound (var <= k**,
+    var <= k** - partial sum Z^2, var >= noise): coordinates are bit-identical and densities agree to rounding between the
+    staged gate (default), the single-stage gate and the full computation (the rows that still go through the variance
+    GEMM may use a different n-split, i.e. a different summation order of the same terms); rows must have been skipped,
+    and some rows must have needed the second stage."""
     from gaussian_process_liouville_equation_b200 import _lib as L
 
     ctx = L.default_context()
-    n, centre = 300, (-0.8, syn.P0)
+    n, centre = 700, (-0.8, syn.P0)
     sets, g = build_models(n, centre, True)
     pts = []
     for e in range(3):
@@ -100,12 +102,20 @@ def test_bound_gated_variance_changes_nothing(dyn):
         pts.append(syn.points_aos(Xe, ye))
     ctx.gate_statistics()
     ctx.set_gated_variance(True)
+    ctx.set_gate_stage_tiles(2)
     a = dyn.evolve(1, pts, syn.MASS, 1.0, g)
-    total, needed, zero = ctx.gate_statistics()
+    total, needed, zero, stage_b = ctx.gate_statistics()
+    ctx.set_gate_stage_tiles(0)
+    c = dyn.evolve(1, pts, syn.MASS, 1.0, g)
+    total0, needed0, zero0, stage_b0 = ctx.gate_statistics()
     ctx.set_gated_variance(False)
     b = dyn.evolve(1, pts, syn.MASS, 1.0, g)
     ctx.set_gated_variance(True)
+    ctx.set_gate_stage_tiles(4)
     for e in range(3):
-        assert np.array_equal(a[e][:, :2], b[e][:, :2])
-        assert np.abs(a[e][:, 2:] - b[e][:, 2:]).max() <= 1e-12 * np.abs(b[e][:, 2:]).max()
+        for other in (a, c):
+            assert np.array_equal(other[e][:, :2], b[e][:, :2])
+            assert np.abs(other[e][:, 2:] - b[e][:, 2:]).max() <= 1e-12 * np.abs(b[e][:, 2:]).max()
     assert total == (8 + 8 + 16) * 5000 and 0 < needed < 0.9 * total and 0 <= zero < total - needed
+    assert 0 < stage_b < 0.5 * needed  # the staged bound decides most of the listed rows
+    assert (total0, needed0, zero0) == (total, needed, zero) and stage_b0 == needed0  # without stages every listed row is computed in full
