@@ -163,6 +163,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     ctx = L.Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    if args.gate_stage_tiles is not None:
+        ctx.set_gate_stage_tiles(args.gate_stage_tiles)
     lib = ctx.lib
     # the three element models of a step are independent: they are factorised concurrently, one context (stream +
     # workspace) per element, from three host threads (the C-ABI is thread-safe across contexts)
@@ -329,7 +331,7 @@ def run_ours(args):
                   "cholesky_inverse_tflops": fa_flops / (fa_ms * 1e-3) / 1e12 if fa_ms > 0 else None, "factorise_share": fa_ms / total_ms,
                   "gated_variance": {"enabled": True, "rows_total": rows_total, "rows_through_variance_gemm": rows_var, "rows_decided_zero": rows_zero, "rows_needing_the_full_variance": rows_b,
                                      "fraction": rows_var / max(rows_total, 1), "fraction_full": rows_b / max(rows_total, 1),
-                                     "note": "exact short-cuts of the cutoff gate (kernel.h:301-332): gate == 1 when |f|^2 >= 4 k** (variance <= prior) or when |f|^2 >= 4 (k** - sum Z^2 over the columns of the first 4 training blocks) (variance <= variance given those points only); gate == 0 when |f|^2 <= noise/2 (variance >= noise); only the undecided queries get the full variance; outputs agree to rounding with the full computation (tests/test_gpu_dynamics.py), whose rate is reported next to it"},
+                                     "note": "exact short-cuts of the cutoff gate (kernel.h:301-332): gate == 1 when |f|^2 >= 4 k** (variance <= prior) or when |f|^2 >= 4 (k** - sum Z^2 over the columns of the first few training blocks) (variance <= variance given those points only); gate == 0 when |f|^2 <= noise/2 (variance >= noise); only the undecided queries get the full variance; outputs agree to rounding with the full computation (tests/test_gpu_dynamics.py), whose rate is reported next to it"},
                   "value_with_every_variance_computed": 1000.0 / (full_ms / args.steps), "ms_per_step_with_every_variance_computed": full_ms / args.steps,
                   "reference_formulation_tflops_equiv": alg_flops_step / ((full_ms / args.steps) * 1e-3) / 1e12,
                   "check": last_scalars},
@@ -350,6 +352,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gate-stage-tiles", type=int, default=None, help="override GPLE_OPT_GATE_STAGE_TILES (tuning)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2 (default, BASELINE.json configs[1]); c4 = configs[3]: ECR, N=4096, 1e6 evolved points/element, meant for --gpus 8")
     args = ap.parse_args()
     if args.workload == "c4":

@@ -261,7 +261,7 @@ extern "C"
 			ctx->gated_variance = value != 0;
 			return GPLE_OK;
 		}
-		if (option == GPLE_OPT_GATE_STAGE_TILES && value >= 0)
+		if (option == GPLE_OPT_GATE_STAGE_TILES && value >= -1)
 		{
 			ctx->gate_stage_tiles = value;
 			return GPLE_OK;

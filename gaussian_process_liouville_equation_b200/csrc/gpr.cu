@@ -1376,7 +1376,8 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		// k** - sum Z^2 over a subset of Z's columns is the posterior variance given only those observations: an upper bound
 		// of the variance that is already close to the noise floor inside the point cloud.
 		const int T = n / 128, Th = m->is_complex ? T / 2 : T;
-		const int stage = std::min(ctx->gate_stage_tiles, Th);
+		// automatic choice: an eighth of the training blocks, between 2 and 8 (profiles/r01_tune_gate_stage.md)
+		const int stage = std::min(ctx->gate_stage_tiles >= 0 ? ctx->gate_stage_tiles : std::max(2, std::min(8, Th / 8)), Th);
 		const bool staged = stage > 0 && stage < Th && count > 0;
 		const TileSet full{0, T, 0, 0};
 		const TileSet setA = !staged ? full : (m->is_complex ? TileSet{0, stage, Th, stage} : TileSet{0, stage, 0, 0});

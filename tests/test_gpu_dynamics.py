@@ -111,7 +111,7 @@ def test_bound_gated_variance_changes_nothing(dyn):
     ctx.set_gated_variance(False)
     b = dyn.evolve(1, pts, syn.MASS, 1.0, g)
     ctx.set_gated_variance(True)
-    ctx.set_gate_stage_tiles(4)
+    ctx.set_gate_stage_tiles(-1)
     for e in range(3):
         for other in (a, c):
             assert np.array_equal(other[e][:, :2], b[e][:, :2])
