@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 	const int N,
 	const int Np,
 	const int n,
+	const int col_limit, // only composite columns [0, col_limit) are generated (the stage-A tile set reads no others)
 	const double* __restrict__ w,
 	double* __restrict__ A,
 	double* __restrict__ pred
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 	double* __restrict__ out = A + size_t(r) * n;
 	if (m >= Q || !valid)
 	{
-		for (int J = lane * 2; J < n; J += 64)
+		for (int J = lane * 2; J < min(n, col_limit); J += 64)
 		{
 			*reinterpret_cast<double2*>(out + J) = make_double2(0.0, 0.0);
 		}
@@ -126,8 +127,9 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 		const GaussBlock g = spec.b[rb][cb];
 		const double* __restrict__ wb = w + cb * Np;
 		double* __restrict__ ob = out + cb * Np;
+		const int jend = min(Np, col_limit - cb * Np); // col_limit is a multiple of 128
 #pragma unroll 4
-		for (int j = lane * 2; j < Np; j += 64)
+		for (int j = lane * 2; j < jend; j += 64)
 		{
 			double2 val = make_double2(0.0, 0.0);
 			if (j < N)
@@ -1385,13 +1387,15 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		double* q = ctx->ws.get<double>("pred.q_all", round_up(size_t(count), 128) + size_t(CHUNK_ROWS) * MAX_VAR_SPLITS);
 		auto sweep = [&](const int* list, const int list_count, const TileSet& ts, double* qout)
 		{
+			// the triangular products of tile t read K* columns [0, (t + 1) * 128): generate no more than the set needs
+			const int cols = 128 * (1 + std::max(ts.c0 > 0 ? ts.b0 + ts.c0 - 1 : 0, ts.c1 > 0 ? ts.b1 + ts.c1 - 1 : 0));
 			for (long long c0 = 0; c0 < list_count; c0 += CHUNK_ROWS)
 			{
 				const int rows_real = int(std::min<long long>(CHUNK_ROWS, list_count - c0));
 				const int rows = int(round_up(size_t(rows_real), 128));
 				{
-					ProfScope prof(ctx, GPLE_PROF_KERNEL_BUILD, 8.0 * double(rows) * n, 1);
-					GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, c0, rows, list, (long long)list_count, Xt2, int(m->N), m->Np, n, m->v, A, nullptr);
+					ProfScope prof(ctx, GPLE_PROF_KERNEL_BUILD, 8.0 * double(rows) * cols, 1);
+					GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, c0, rows, list, (long long)list_count, Xt2, int(m->N), m->Np, n, cols, m->v, A, nullptr);
 				}
 				ProfScope prof(ctx, GPLE_PROF_VARIANCE_GEMM, var_gemm_flops(ts, rows), 1);
 				launch_var_gemm(ctx, g_var_variant, A, m->W, n, rows, qout + c0, ts);
@@ -1446,7 +1450,7 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		{
 			{
 				ProfScope prof(ctx, GPLE_PROF_KERNEL_BUILD, 8.0 * double(rows) * n, 1);
-				GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, row0, rows, nullptr, 0ll, Xt2, int(m->N), m->Np, n, m->v, A, pred);
+				GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, row0, rows, nullptr, 0ll, Xt2, int(m->N), m->Np, n, n, m->v, A, pred);
 			}
 			ProfScope prof(ctx, GPLE_PROF_VARIANCE_GEMM, double(rows) * n * (double(n) + 128.0), 1);
 			launch_var_gemm(ctx, g_var_variant, A, m->W, n, rows, q, TileSet{0, n / 128, 0, 0});
