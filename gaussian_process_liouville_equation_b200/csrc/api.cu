@@ -266,6 +266,11 @@ extern "C"
 			ctx->gate_stage_tiles = value;
 			return GPLE_OK;
 		}
+		if (option == GPLE_OPT_GATE_STAGE_TILES_IM && value >= -1)
+		{
+			ctx->gate_stage_tiles_im = value;
+			return GPLE_OK;
+		}
 		return GPLE_ERR_ARG;
 	}
 

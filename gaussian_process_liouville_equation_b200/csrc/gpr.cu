@@ -1378,12 +1378,14 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		// k** - sum Z^2 over a subset of Z's columns is the posterior variance given only those observations: an upper bound
 		// of the variance that is already close to the noise floor inside the point cloud.
 		const int T = n / 128, Th = m->is_complex ? T / 2 : T;
-		// automatic choice: an eighth of the training blocks, between 2 and 8 (profiles/r01_tune_gate_stage.md)
-		const int stage = std::min(ctx->gate_stage_tiles >= 0 ? ctx->gate_stage_tiles : std::max(2, std::min(8, Th / 8)), Th);
+		// automatic choice: a quarter of the training blocks, between 2 and 8; for the complex element a quarter as many blocks of
+		// Im rows (each of them costs a product over ALL Re columns, and they tighten the bound little) (profiles/r01_tune_gate_stage.md)
+		const int stage = std::min(ctx->gate_stage_tiles >= 0 ? ctx->gate_stage_tiles : std::max(2, std::min(8, Th / 4)), Th);
 		const bool staged = stage > 0 && stage < Th && count > 0;
 		const TileSet full{0, T, 0, 0};
-		const TileSet setA = !staged ? full : (m->is_complex ? TileSet{0, stage, Th, stage} : TileSet{0, stage, 0, 0});
-		const TileSet setB = m->is_complex ? TileSet{stage, Th - stage, Th + stage, Th - stage} : TileSet{stage, T - stage, 0, 0};
+		const int stage_im = std::min(ctx->gate_stage_tiles_im >= 0 ? ctx->gate_stage_tiles_im : std::max(1, stage / 4), Th);
+		const TileSet setA = !staged ? full : (m->is_complex ? TileSet{0, stage, Th, stage_im} : TileSet{0, stage, 0, 0});
+		const TileSet setB = m->is_complex ? TileSet{stage, Th - stage, Th + stage_im, Th - stage_im} : TileSet{stage, T - stage, 0, 0};
 		double* q = ctx->ws.get<double>("pred.q_all", round_up(size_t(count), 128) + size_t(CHUNK_ROWS) * MAX_VAR_SPLITS);
 		auto sweep = [&](const int* list, const int list_count, const TileSet& ts, double* qout)
 		{

@@ -70,16 +70,17 @@ extern "C"
 	 *   |f|^2 <= sigma_f^2 sigma_n^2 / 2 => gate == 0  (var >= sigma_f^2 sigma_n^2 for a query that coincides with no
 	 *                                                   training point; only used while the noise is >= 1e-9 k**).
 	 * The undecided queries then meet a STAGED bound: sum Z^2 over the columns of Z = K* L^-T that belong to the first
-	 * GPLE_OPT_GATE_STAGE_TILES (default -1 = automatic: an eighth of the blocks, between 2 and 8) 128-blocks of training points is the variance explained by those points alone, so
+	 * GPLE_OPT_GATE_STAGE_TILES (default -1 = automatic: a quarter of the blocks, between 2 and 8) 128-blocks of training points is the variance explained by those points alone, so
 	 *   |f|^2 >= 4 (k** - partial sum)  => gate == 1,
 	 * and only the queries this does not decide see the remaining columns (the triangular products of the first blocks are
-	 * the short ones: 2 of 16 blocks cost 1/64 of the flops).  The decided queries get exactly the value the full computation
+	 * the short ones: 4 of 16 blocks cost 1/14 of the flops).  The decided queries get exactly the value the full computation
 	 * gives; the others go through the variance GEMM in a different batch composition (summation order inside the GEMM may
 	 * differ).  GPLE_OPT_GATED_VARIANCE = 0 forces every variance; GPLE_OPT_GATE_STAGE_TILES = 0 disables the staged bound. */
 	enum gple_option
 	{
 		GPLE_OPT_GATED_VARIANCE = 1,
-		GPLE_OPT_GATE_STAGE_TILES = 2
+		GPLE_OPT_GATE_STAGE_TILES = 2,
+		GPLE_OPT_GATE_STAGE_TILES_IM = 3 /* complex element: blocks of Im rows in the stage (default -1 = a quarter of the Re blocks, at least 1) */
 	};
 	int gple_ctx_set_option(gple_ctx* ctx, int option, int value);
 	/* Gated predictions since the last call (then reset): out = {composite rows seen, rows sent through stage A of the
