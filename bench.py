@@ -156,7 +156,10 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL prints its version banner on stdout otherwise; stdout carries exactly one JSON line
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -339,7 +342,7 @@ def run_ours(args):
         step_s, desc, cores = cpu_sample(sets)
         line["cpu_baseline"] = {"value": 1.0 / step_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
