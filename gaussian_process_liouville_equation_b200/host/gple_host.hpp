@@ -21,6 +21,7 @@
 #include <limits>
 #include <memory>
 #include <optional>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -472,6 +473,48 @@ inline void evolve(AllPoints& density, double mass, double dt, const TrainingKer
 		gple_evolve(Context::get(), pes_model, kernels.handle(0), kernels.handle(1), kernels.handle(2), reinterpret_cast<double*>(density[0].data()), density[0].size(), reinterpret_cast<double*>(density[1].data()), density[1].size(), reinterpret_cast<double*>(density[2].data()), density[2].size(), mass, dt),
 		"evolve"
 	);
+}
+
+/// output_phase (gple/output.cpp:181-233): cutoff prediction (two lines: real and imaginary part) and variance (one line) of
+/// every element on the output grid, elements in lower-triangular order, absent elements as zeros; values separated by single
+/// blanks at the stream's precision like Eigen's VectorFormatter (gple/stdafx.h:129); a blank line closes each record.
+inline void output_phase(std::ostream& phase, std::ostream& variance, const TrainingKernels& AllKernels, const PhasePoints& PhaseGrids)
+{
+	const std::size_t NumPoints = PhaseGrids.cols();
+	auto line = [NumPoints](std::ostream& os, auto&& value)
+	{
+		for (std::size_t i = 0; i < NumPoints; i++)
+		{
+			os << (i == 0 ? "" : " ") << value(i);
+		}
+		os << '\n';
+	};
+	auto zero = [](std::size_t) { return 0.0; };
+	for (std::size_t e = 0; e < NumElements; e++)
+	{
+		if (e != 1 && AllKernels.Diagonal[e / 2])
+		{
+			const PredictiveKernel k(PhaseGrids, *AllKernels.Diagonal[e / 2], false);
+			line(phase, [&k](std::size_t i) { return k.get_cutoff_prediction()[i]; });
+			line(phase, zero);
+			line(variance, [&k](std::size_t i) { return k.get_variance()[i]; });
+		}
+		else if (e == 1 && AllKernels.OffDiagonal)
+		{
+			const PredictiveComplexKernel ck(PhaseGrids, *AllKernels.OffDiagonal, false);
+			line(phase, [&ck](std::size_t i) { return ck.get_cutoff_prediction()[i].real(); });
+			line(phase, [&ck](std::size_t i) { return ck.get_cutoff_prediction()[i].imag(); });
+			line(variance, [&ck](std::size_t i) { return ck.get_variance()[i]; });
+		}
+		else
+		{
+			line(phase, zero);
+			line(phase, zero);
+			line(variance, zero);
+		}
+	}
+	phase << '\n';
+	variance << '\n';
 }
 
 /// gple/pes.h:47 (one position)

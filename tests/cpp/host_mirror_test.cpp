@@ -5,10 +5,12 @@
 
 #include <cmath>
 #include <cstdio>
+#include <fstream>
+#include <iomanip>
 
 using namespace gple_host;
 
-int main()
+int main(int argc, char** argv)
 {
 	const std::size_t n = 200;
 	const double sx = 1.0 / (2.0 * 0.7056), sp = 0.7056, p0 = 14.112;
@@ -42,6 +44,23 @@ int main()
 	q(1, 1) = p0;
 	const PredictiveKernel pk(q, *kernels.Diagonal[0], false);
 	std::printf("cutoff0 %.17g\ncutoff1 %.17g\nvar0 %.17g\n", pk.get_cutoff_prediction()[0], pk.get_cutoff_prediction()[1], pk.get_variance()[0]);
+	if (argc > 1)
+	{
+		// gple/main.cpp:118 output_phase on a small grid (gple/input.cpp:39-71 builds it the same way: x-major)
+		PhasePoints grid(5 * 4);
+		for (std::size_t ix = 0; ix < 5; ix++)
+		{
+			for (std::size_t ip = 0; ip < 4; ip++)
+			{
+				grid(0, ix * 4 + ip) = -0.8 + sx * (double(ix) - 2.0);
+				grid(1, ix * 4 + ip) = p0 + sp * (double(ip) - 1.5) * 1.5;
+			}
+		}
+		std::ofstream phase(std::string(argv[1]) + "/phase.txt"), variance(std::string(argv[1]) + "/var.txt");
+		phase << std::setprecision(17);
+		variance << std::setprecision(17);
+		output_phase(phase, variance, kernels, grid);
+	}
 	evolve(density, 2000.0, 2.0, kernels, GPLE_DAC);
 	std::printf("x00_0 %.17g\nrho00_0 %.17g\nrho10_5_re %.17g\nrho10_5_im %.17g\n", density[0][0].r[0], density[0][0].rho.real(), density[1][5].rho.real(), density[1][5].rho.imag());
 	const auto pop = calculate_population_each_surface(density, 2000.0, GPLE_DAC);

@@ -23,9 +23,9 @@ def test_host_mirror_compiles_and_links():
 
 
 @pytest.mark.gpu
-def test_host_mirror_matches_oracle(oracle):
+def test_host_mirror_matches_oracle(oracle, tmp_path):
     build()
-    out = subprocess.run([EXE], capture_output=True, text=True, check=True).stdout
+    out = subprocess.run([EXE, str(tmp_path)], capture_output=True, text=True, check=True).stdout
     got = {k: float(v) for k, v in (line.split() for line in out.strip().splitlines())}
     n, sx, sp, p0 = 200, 1.0 / (2.0 * 0.7056), 0.7056, 14.112
     i = np.arange(1, n + 1)
@@ -50,3 +50,13 @@ def test_host_mirror_matches_oracle(oracle):
     assert got["rho10_5_re"] == pytest.approx(ev[1][5, 2], abs=1e-6 * sc) and got["rho10_5_im"] == pytest.approx(ev[1][5, 3], abs=1e-6 * sc)
     E, _, _ = oracle.pes(1, np.array([0.3]))
     assert got["E1_at_0.3"] == pytest.approx(E[0, 1], rel=1e-14)
+    # output_phase (gple/output.cpp:181-233): 3 elements x (Re, Im) cutoff-prediction lines + 3 variance lines, blank-line terminated
+    grid = np.array([[-0.8 + sx * (ix - 2.0), p0 + sp * (ip - 1.5) * 1.5] for ix in range(5) for ip in range(4)])
+    phase = [np.array(line.split(), dtype=float) for line in (tmp_path / "phase.txt").read_text().split("\n")[:6]]
+    var = [np.array(line.split(), dtype=float) for line in (tmp_path / "var.txt").read_text().split("\n")[:3]]
+    assert (tmp_path / "phase.txt").read_text().endswith("\n\n") and all(len(v) == 20 for v in phase + var)
+    for e, k in enumerate((k0, k1, k2)):
+        p = k.predict(grid)
+        scale = np.abs(p["cutoff"]).max()
+        assert np.abs(phase[2 * e] - p["cutoff"].real).max() <= 1e-6 * scale and np.abs(phase[2 * e + 1] - p["cutoff"].imag).max() <= 1e-6 * scale
+        assert np.abs(var[e] - p["var"]).max() <= 1e-9 * (tr[0] ** 2 if e != 1 else tc[0] ** 2 * (tc[1] ** 2 + tc[4] ** 2))
