@@ -198,6 +198,9 @@ extern "C"
 			[&]() -> int
 			{
 				GPLE_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+				GPLE_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+				GPLE_CUDA(cudaEventCreateWithFlags(&ctx->ev_panel, cudaEventDisableTiming));
+				GPLE_CUDA(cudaEventCreateWithFlags(&ctx->ev_bulk, cudaEventDisableTiming));
 				ctx->stream = ctx->own_stream;
 				ctx->h_pinned_count = 512;
 				GPLE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pinned), ctx->h_pinned_count * sizeof(double)));
@@ -231,6 +234,12 @@ extern "C"
 		if (ctx->h_pinned != nullptr)
 		{
 			cudaFreeHost(ctx->h_pinned);
+		}
+		if (ctx->aux_stream != nullptr)
+		{
+			cudaStreamDestroy(ctx->aux_stream);
+			cudaEventDestroy(ctx->ev_panel);
+			cudaEventDestroy(ctx->ev_bulk);
 		}
 		if (ctx->own_stream != nullptr)
 		{

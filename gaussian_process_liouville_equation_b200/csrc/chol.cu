@@ -488,30 +488,69 @@ struct Chol
 		GPLE_LAUNCH(ctx, potrf_leaf_kernel, 1, LEAF_THREADS, LEAF_SMEM, at(o, o), ld, dinv + size_t(o / LEAF) * LEAF * LEAF, info, o);
 	}
 
+	/// rank-128 update C -= P P^T of the lower 128-tiles of a trailing block (C: m x nc at (r, c); P: the panel rows r.. and c..)
+	void syrk(const int r, const int c, const int m, const int nc, const int pcol) const
+	{
+		gemm::GemmArgs g{};
+		g.A = at(r, pcol);
+		g.B = at(c, pcol);
+		g.C = at(r, c);
+		g.lda = g.ldb = g.ldc = ld;
+		g.M = m;
+		g.N = nc;
+		g.K = LEAF;
+		g.alpha = -1.0;
+		g.beta = 1.0;
+		g.lower_only = (r == c && m == nc) ? 1 : 0;
+		run_gemm(ctx, false, g);
+	}
+
 	/// Right-looking sweep over 128-blocks (every GEMM has K = 128): the latency-optimal order for blocks of up to a few
-	/// thousand rows, where the recursive form leaves most SMs idle behind a few long-K tiles.
+	/// thousand rows, where the recursive form leaves most SMs idle behind a few long-K tiles.  With LOOK-AHEAD: after the
+	/// panel solve of step k only block column k + 1 is updated on the main stream (that is all leaf k + 1 and its panel
+	/// solve need); the bulk of the trailing update (columns k + 2 ...) runs on the context's auxiliary stream underneath
+	/// the next leaf, which is a single-CTA kernel.  Ordering: bulk(k) waits for the panel of step k; the column update of
+	/// step k + 1 waits for bulk(k) (both write column k + 2).
 	void potrf_flat(const int o, const int n) const
 	{
+		const bool lookahead = n >= 4 * LEAF && ctx->aux_stream != nullptr;
+		cudaStream_t main = ctx->stream;
+		bool bulk_pending = false;
 		for (int k = 0; k < n; k += LEAF)
 		{
 			leaf(o + k);
 			const int rest = n - k - LEAF;
-			if (rest > 0)
+			if (rest <= 0)
 			{
-				trsm(o + k + LEAF, rest, o + k, LEAF);
-				gemm::GemmArgs g{};
-				g.A = at(o + k + LEAF, o + k);
-				g.B = at(o + k + LEAF, o + k);
-				g.C = at(o + k + LEAF, o + k + LEAF);
-				g.lda = g.ldb = g.ldc = ld;
-				g.M = rest;
-				g.N = rest;
-				g.K = LEAF;
-				g.alpha = -1.0;
-				g.beta = 1.0;
-				g.lower_only = 1;
-				run_gemm(ctx, false, g);
+				break;
 			}
+			trsm(o + k + LEAF, rest, o + k, LEAF);
+			if (!lookahead || rest == LEAF)
+			{
+				if (bulk_pending)
+				{
+					GPLE_CUDA(cudaStreamWaitEvent(main, ctx->ev_bulk, 0));
+					bulk_pending = false;
+				}
+				syrk(o + k + LEAF, o + k + LEAF, rest, rest, o + k);
+				continue;
+			}
+			GPLE_CUDA(cudaEventRecord(ctx->ev_panel, main));
+			if (bulk_pending)
+			{
+				GPLE_CUDA(cudaStreamWaitEvent(main, ctx->ev_bulk, 0)); // bulk(k - 1) also wrote block column k + 1
+			}
+			syrk(o + k + LEAF, o + k + LEAF, rest, LEAF, o + k); // block column k + 1: all the next leaf and panel solve read
+			ctx->stream = ctx->aux_stream;
+			GPLE_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_panel, 0));
+			syrk(o + k + 2 * LEAF, o + k + 2 * LEAF, rest - LEAF, rest - LEAF, o + k);
+			GPLE_CUDA(cudaEventRecord(ctx->ev_bulk, ctx->aux_stream));
+			ctx->stream = main;
+			bulk_pending = true;
+		}
+		if (bulk_pending)
+		{
+			GPLE_CUDA(cudaStreamWaitEvent(main, ctx->ev_bulk, 0));
 		}
 	}
 

@@ -125,6 +125,9 @@ struct gple_ctx
 {
 	int device = 0;
 	cudaStream_t own_stream = nullptr;
+	// look-ahead of the factorisation: the bulk of a trailing update runs here while the next leaf runs on `stream`
+	cudaStream_t aux_stream = nullptr;
+	cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr;
 	cudaStream_t stream = nullptr;
 	unsigned long long launches = 0;
 	std::string last_error;
