@@ -1,0 +1,100 @@
+// The reference's main loop (gple/main.cpp:19-202) written against the C++ host headers of this repo: initial Metropolis
+// selection from the analytic Wigner distribution, hyper-parameter optimisation, then per tick
+//   evolve(density), evolve(extra_points) -> is_very_small -> [new element selection + optimisation] ->
+//   [routine / average-triggered re-optimisation] -> TrainingKernels rebuild
+// with every numerical step on the GPU through the C-ABI.  Output: one "tick population energy purity" line per tick
+// (the quantities of output_average / spdlog in main.cpp:117-126) and a summary.
+//
+//   mqcle_run N ticks reopt_freq pes_model(0 SAC, 1 DAC, 2 ECR) [seed] [x0]
+#include "../gaussian_process_liouville_equation_b200/host/gple_mc.hpp"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
+using namespace gple_host;
+
+int main(int argc, char** argv)
+{
+	if (argc < 5)
+	{
+		std::fprintf(stderr, "usage: mqcle_run N ticks reopt_freq pes_model [seed] [x0]\n");
+		return 2;
+	}
+	const std::size_t NumPoints = std::strtoull(argv[1], nullptr, 10), TotalTicks = std::strtoull(argv[2], nullptr, 10), ReoptFreq = std::strtoull(argv[3], nullptr, 10);
+	const int pes_model = std::atoi(argv[4]);
+	const unsigned long long seed = argc > 5 ? std::strtoull(argv[5], nullptr, 10) : 20240229ull;
+	const std::size_t NumExtraPoints = NumPoints * 5; // main.cpp:35
+	// test/continue_test.cpp:41, test/stdafx.h:51
+	const double mass = 2000.0, dt = 1.0, sp = 0.7056, sx = 1.0 / (2.0 * sp);
+	const ClassicalPhaseVector r0{argc > 6 ? std::atof(argv[6]) : -10.0, 14.112}, SigmaR0{sx, sp};
+	std::mt19937_64 engine(seed);
+	const auto begin = std::chrono::steady_clock::now();
+
+	// main.cpp:36-57: N copies of r0, then the Metropolis walk in the initial distribution
+	std::array<MCParameters, NumElements> MCParams;
+	Sampler initdist(seed, r0, SigmaR0, {1.0, 0.0}, {0.0, 0.0});
+	AllPoints density;
+	density[0].assign(NumPoints, PhaseSpacePoint{r0, {0.0, 0.0}});
+	std::array<bool, NumElements> IsSmall{false, true, true};
+	monte_carlo_selection(density, MCParams, initdist);
+	// main.cpp:58-69
+	const double TotalEnergy = calculate_total_energy_average_each_surface(density, mass, pes_model)[0];
+	const double Purity = 1.0;
+	AllPoints extra_points = generate_extra_points(density, NumExtraPoints, initdist, engine, mass, pes_model);
+	// main.cpp:70-74
+	Optimization optimizer(SigmaR0, {20.0, 40.0}, mass, pes_model, TotalEnergy, Purity);
+	optimizer.set_maximum_evaluations(300, 600);
+	Optimization::Result opt_result = optimizer.optimize(density, extra_points);
+	std::unique_ptr<TrainingKernels> all_kernels = std::make_unique<TrainingKernels>(optimizer.get_parameters(), density);
+	std::size_t optimisations = 1;
+	auto output = [&](const std::size_t tick)
+	{
+		const QuantumVectorD E = calculate_total_energy_average_each_surface(density, mass, pes_model);
+		std::printf("tick %zu %.15e %.15e %.15e\n", tick, all_kernels->calculate_population(), all_kernels->calculate_total_energy_average(E), all_kernels->calculate_purity());
+	};
+	output(0);
+	std::printf("displacement %.17g\nmc_steps %zu\n", MCParams[0].get_max_displacement(), MCParams[0].get_num_MC_steps());
+
+	// main.cpp:135-202
+	for (std::size_t iTick = 1; iTick <= TotalTicks; iTick++)
+	{
+		const std::array<bool, NumElements> IsSmallOld = IsSmall;
+		evolve(density, mass, dt, *all_kernels, pes_model);
+		evolve(extra_points, mass, dt, *all_kernels, pes_model);
+		IsSmall = is_very_small(density, mass, dt, *all_kernels, pes_model);
+		bool IsOptimized = false;
+		auto reoptimize = [&]()
+		{
+			opt_result = optimizer.optimize(density, extra_points);
+			all_kernels = std::make_unique<TrainingKernels>(optimizer.get_parameters(), density);
+			Sampler predict(seed + iTick, *all_kernels);
+			extra_points = generate_extra_points(density, NumExtraPoints, predict, engine, mass, pes_model);
+			IsOptimized = true;
+			optimisations++;
+		};
+		if (IsSmallOld != IsSmall)
+		{
+			Sampler new_point(seed + iTick, *all_kernels, pes_model, mass, dt); // main.cpp:153-156
+			new_element_point_selection(density, extra_points, IsSmallOld, IsSmall, MCParams, new_point, engine, mass, pes_model);
+			reoptimize();
+		}
+		if (ReoptFreq > 0 && iTick % ReoptFreq == 0 && !IsOptimized)
+		{
+			reoptimize();
+		}
+		if (!IsOptimized)
+		{
+			all_kernels = std::make_unique<TrainingKernels>(optimizer.get_parameters(), density);
+			const double pop = all_kernels->calculate_population(), pur = all_kernels->calculate_purity();
+			if (pur > (1.0 + 2.0 * AverageTolerance) * Purity || pop > 1.0 + 2.0 * AverageTolerance || pop < 1.0 - 2.0 * AverageTolerance)
+			{
+				reoptimize(); // main.cpp:176-186
+			}
+		}
+		output(iTick);
+	}
+	const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - begin).count();
+	std::printf("elements %zu %zu %zu\noptimisations %zu\nwall_s %.3f\n", density[0].size(), density[1].size(), density[2].size(), optimisations, wall);
+	return 0;
+}

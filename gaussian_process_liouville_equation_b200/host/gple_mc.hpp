@@ -7,9 +7,10 @@
 // Philox stream per chain; a Sampler folds a call counter into the stream id, so successive walks are independent and the
 // whole sequence is a pure function of the seed.  Header-only; link with libgple_b200.so.
 #pragma once
-#include "gple_host.hpp"
+#include "gple_opt.hpp"
 
 #include <cmath>
+#include <random>
 
 namespace gple_host
 {
@@ -76,6 +77,18 @@ public:
 			"markov chains"
 		);
 		return accept;
+	}
+	/// distribution(r, RowIndex, ColIndex) at the coordinates of `pts` (their densities are overwritten); no walk, no draw
+	void relabel(ElementPoints& pts, const std::size_t RowIndex, const std::size_t ColIndex) const
+	{
+		if (pts.empty())
+		{
+			return;
+		}
+		gple_mc_source s = src;
+		s.row = int(RowIndex);
+		s.col = int(ColIndex);
+		Context::check(gple_markov_chains(Context::get(), &s, reinterpret_cast<double*>(pts.data()), pts.size(), 0, 1.0, seed, 0, 0, nullptr, nullptr), "relabel");
 	}
 	/// gple/mc.cpp:187-203
 	std::vector<double> autocorrelation(const std::vector<double>& chain_states, const std::size_t NumChains, const std::size_t Length) const
@@ -184,6 +197,122 @@ inline void monte_carlo_selection(AllPoints& density, std::array<MCParameters, N
 		if (!density[e].empty())
 		{
 			element_monte_carlo(density[e], MCParams[e], sampler, Row[e], Col[e]);
+		}
+	}
+}
+/// generate_extra_points (gple/mc.cpp:59-120): training point (cyclic) + N(0, sigma_element) jitter per dimension, labelled
+/// with the current distribution -- one batched evaluation per element instead of NumExtraPoints single-point calls.
+/// Host-side randomness (the jitter) comes from the caller's engine, as the reference draws it from its global one.
+template <typename Engine>
+inline AllPoints generate_extra_points(const AllPoints& density, const std::size_t NumExtraPoints, const Sampler& sampler, Engine& engine, const double mass, const int pes_model)
+{
+	static constexpr std::size_t Row[NumElements] = {0, 1, 1}, Col[NumElements] = {0, 0, 1};
+	AllPoints result;
+	for (std::size_t e = 0; e < NumElements; e++)
+	{
+		if (density[e].empty())
+		{
+			continue;
+		}
+		const ClassicalPhaseVector sd = calculate_standard_deviation_one_surface(density[e], mass, pes_model);
+		std::array<std::normal_distribution<double>, PhaseDim> normdists{std::normal_distribution<double>(0.0, sd[0]), std::normal_distribution<double>(0.0, sd[1])};
+		result[e].resize(NumExtraPoints);
+		for (std::size_t i = 0; i < NumExtraPoints; i++)
+		{
+			result[e][i].r = density[e][i % density[e].size()].r;
+			for (std::size_t d = 0; d < PhaseDim; d++)
+			{
+				result[e][i].r[d] += normdists[d](engine);
+			}
+		}
+		sampler.relabel(result[e], Row[e], Col[e]);
+	}
+	return result;
+}
+
+/// is_very_small (gple/evolve.cpp:445-478): an EMPTY element is small iff new_point_predict at all test points (the rho00
+/// points) has |rho|^2 below (1e-5)^2; a populated element is never small.
+inline std::array<bool, NumElements> is_very_small(const AllPoints& density, const double mass, const double dt, const TrainingKernels& kernels, const int pes_model)
+{
+	static constexpr int Row[NumElements] = {0, 1, 1}, Col[NumElements] = {0, 0, 1};
+	static constexpr double epsilon = 1e-5 * 1e-5;
+	std::array<bool, NumElements> result{false, false, false};
+	for (std::size_t e = 0; e < NumElements; e++)
+	{
+		if (!density[e].empty() || density[0].empty())
+		{
+			continue;
+		}
+		const std::size_t n = density[0].size();
+		std::vector<double> r(2 * n), rho(2 * n);
+		for (std::size_t i = 0; i < n; i++)
+		{
+			r[2 * i] = density[0][i].r[0];
+			r[2 * i + 1] = density[0][i].r[1];
+		}
+		Context::check(gple_new_point_predict(Context::get(), pes_model, kernels.handle(0), kernels.handle(1), kernels.handle(2), r.data(), n, Row[e], Col[e], mass, dt, rho.data()), "is_very_small");
+		bool small = true;
+		for (std::size_t i = 0; i < n && small; i++)
+		{
+			small = rho[2 * i] * rho[2 * i] + rho[2 * i + 1] * rho[2 * i + 1] < epsilon;
+		}
+		result[e] = small;
+	}
+	return result;
+}
+
+/// new_element_point_selection (gple/mc.cpp:407-537): a newly populated element takes the N most important of all current
+/// coordinates (|rho|^2 of `sampler`'s density: new_point_predict in main.cpp:147-157), replicated up to N, walks them and gets
+/// extra points; a newly small element is emptied.
+template <typename Engine>
+inline void new_element_point_selection(AllPoints& density, AllPoints& extra_points, const std::array<bool, NumElements>& IsSmallOld, const std::array<bool, NumElements>& IsSmall, std::array<MCParameters, NumElements>& MCParams, Sampler& sampler, Engine& engine, const double mass, const int pes_model)
+{
+	static constexpr std::size_t Row[NumElements] = {0, 1, 1}, Col[NumElements] = {0, 0, 1};
+	if (IsSmallOld == IsSmall)
+	{
+		return;
+	}
+	const std::size_t NumPoints = density[0].size(), NumExtraPoints = extra_points[0].size();
+	ElementPoints PossibleCoordinates;
+	for (std::size_t e = 0; e < NumElements; e++)
+	{
+		PossibleCoordinates.insert(PossibleCoordinates.end(), density[e].cbegin(), density[e].cend());
+		PossibleCoordinates.insert(PossibleCoordinates.end(), extra_points[e].cbegin(), extra_points[e].cend());
+	}
+	for (std::size_t e = 0; e < NumElements; e++)
+	{
+		if (IsSmallOld[e] && !IsSmall[e])
+		{
+			ElementPoints element_density = PossibleCoordinates;
+			sampler.relabel(element_density, Row[e], Col[e]);
+			const std::size_t NumNonZeroPoints = std::size_t(std::count_if(element_density.cbegin(), element_density.cend(), [](const PhaseSpacePoint& psp) { return psp.rho != 0.0; }));
+			const std::size_t keep = std::min(NumPoints, NumNonZeroPoints);
+			if (keep == 0)
+			{
+				continue;
+			}
+			std::nth_element(element_density.begin(), element_density.begin() + keep, element_density.end(), [](const PhaseSpacePoint& a, const PhaseSpacePoint& b) { return std::norm(a.rho) > std::norm(b.rho); });
+			element_density.resize(keep);
+			while (NumPoints >= 2 * element_density.size())
+			{
+				const ElementPoints copy = element_density;
+				element_density.insert(element_density.end(), copy.cbegin(), copy.cend());
+			}
+			if (element_density.size() < NumPoints)
+			{
+				const ElementPoints copy(element_density.cbegin(), element_density.cbegin() + (NumPoints - element_density.size()));
+				element_density.insert(element_density.end(), copy.cbegin(), copy.cend());
+			}
+			element_monte_carlo(element_density, MCParams[e], sampler, Row[e], Col[e]);
+			density[e] = std::move(element_density);
+			AllPoints only;
+			only[e] = density[e];
+			extra_points[e] = generate_extra_points(only, NumExtraPoints, sampler, engine, mass, pes_model)[e];
+		}
+		else if (!IsSmallOld[e] && IsSmall[e])
+		{
+			density[e].clear();
+			extra_points[e].clear();
 		}
 	}
 }
