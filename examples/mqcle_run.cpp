@@ -48,6 +48,9 @@ int main(int argc, char** argv)
 	Optimization::Result opt_result = optimizer.optimize(density, extra_points);
 	std::unique_ptr<TrainingKernels> all_kernels = std::make_unique<TrainingKernels>(optimizer.get_parameters(), density);
 	std::size_t optimisations = 1;
+	double t_opt = 0.0, t_evolve = 0.0, t_rebuild = 0.0, t_select = 0.0;
+	auto now = []() { return std::chrono::steady_clock::now(); };
+	auto since = [](const std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
 	auto output = [&](const std::size_t tick)
 	{
 		const QuantumVectorD E = calculate_total_energy_average_each_surface(density, mass, pes_model);
@@ -60,13 +63,17 @@ int main(int argc, char** argv)
 	for (std::size_t iTick = 1; iTick <= TotalTicks; iTick++)
 	{
 		const std::array<bool, NumElements> IsSmallOld = IsSmall;
+		auto t0 = now();
 		evolve(density, mass, dt, *all_kernels, pes_model);
 		evolve(extra_points, mass, dt, *all_kernels, pes_model);
 		IsSmall = is_very_small(density, mass, dt, *all_kernels, pes_model);
+		t_evolve += since(t0);
 		bool IsOptimized = false;
 		auto reoptimize = [&]()
 		{
+			const auto t1 = now();
 			opt_result = optimizer.optimize(density, extra_points);
+			t_opt += since(t1);
 			all_kernels = std::make_unique<TrainingKernels>(optimizer.get_parameters(), density);
 			Sampler predict(seed + iTick, *all_kernels);
 			extra_points = generate_extra_points(density, NumExtraPoints, predict, engine, mass, pes_model);
@@ -75,8 +82,10 @@ int main(int argc, char** argv)
 		};
 		if (IsSmallOld != IsSmall)
 		{
+			t0 = now();
 			Sampler new_point(seed + iTick, *all_kernels, pes_model, mass, dt); // main.cpp:153-156
 			new_element_point_selection(density, extra_points, IsSmallOld, IsSmall, MCParams, new_point, engine, mass, pes_model);
+			t_select += since(t0);
 			reoptimize();
 		}
 		if (ReoptFreq > 0 && iTick % ReoptFreq == 0 && !IsOptimized)
@@ -85,7 +94,9 @@ int main(int argc, char** argv)
 		}
 		if (!IsOptimized)
 		{
+			t0 = now();
 			all_kernels = std::make_unique<TrainingKernels>(optimizer.get_parameters(), density);
+			t_rebuild += since(t0);
 			const double pop = all_kernels->calculate_population(), pur = all_kernels->calculate_purity();
 			if (pur > (1.0 + 2.0 * AverageTolerance) * Purity || pop > 1.0 + 2.0 * AverageTolerance || pop < 1.0 - 2.0 * AverageTolerance)
 			{
@@ -96,5 +107,6 @@ int main(int argc, char** argv)
 	}
 	const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - begin).count();
 	std::printf("elements %zu %zu %zu\noptimisations %zu\nwall_s %.3f\n", density[0].size(), density[1].size(), density[2].size(), optimisations, wall);
+	std::printf("seconds_evolve %.4f\nseconds_rebuild %.4f\nseconds_optimise_in_loop %.4f\nseconds_new_element_selection %.4f\n", t_evolve, t_rebuild, t_opt, t_select);
 	return 0;
 }
