@@ -66,6 +66,7 @@ SIGNATURES = {
     "gple_model_destroy": (C.c_int, [_vp, _vp]),
     "gple_predict_real": (C.c_int, [_vp, _vp, _dp, _sz, _dp, _dp, _dp, _dp, _dp, _dp]),
     "gple_predict_complex": (C.c_int, [_vp, _vp, _dp, _sz, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "gple_validation_error": (C.c_int, [_vp, _vp, _dp, _dp, _sz, _dp, _dp]),
     "gple_loose_function": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp, _dp, _sz, _dp, _dp, _sz, _dp]),
     "gple_pes": (C.c_int, [_vp, C.c_int, _dp, _sz, _dp, _dp, _dp]),
     "gple_evolve": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, _dp, _sz, _dp, _sz, C.c_double, C.c_double]),

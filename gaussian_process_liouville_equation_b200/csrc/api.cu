@@ -171,6 +171,34 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, const int i
 }
 } // namespace
 
+namespace
+{
+/// Validation half of loose_function (opt.cpp:455-470): squared error of the raw prediction on the extra set and, optionally,
+/// its gradient (kernel.cpp:519-541 / complex_kernel.cpp:645-667).  Xe / ye: host or device; ye complex interleaved.
+void validation_error(gple_ctx* ctx, const gple_model* m, const double* Xe, const double* ye, const size_t M, double* error, double* grad)
+{
+	const size_t w = m->is_complex ? 2 : 1;
+	DeviceArray<double> xe(ctx, Xe, 2 * M, false), yc(ctx, ye, 2 * M, false);
+	// opt.cpp:451: the real kernel sees ExtraTrainingLabel.real()
+	double* yq = yc.dev;
+	if (!m->is_complex)
+	{
+		yq = ctx->ws.get<double>("loose.yre", M);
+		GPLE_CUDA(cudaMemcpy2DAsync(yq, sizeof(double), yc.dev, 2 * sizeof(double), sizeof(double), M, cudaMemcpyDeviceToDevice, ctx->stream));
+	}
+	double* d_err = ctx->ws.get<double>("pred.err", 8);
+	double* d_cut = grad != nullptr ? ctx->ws.get<double>("pred.cut_tmp", w * M) : nullptr;
+	predict_device(ctx, m, xe.dev, M, yq, nullptr, nullptr, d_cut, d_err);
+	GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 128, d_err, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	sync(ctx);
+	*error = ctx->h_pinned[128];
+	if (grad != nullptr)
+	{
+		validation_gradient(ctx, m, xe.dev, M, yq, d_cut, grad);
+	}
+}
+} // namespace
+
 extern "C"
 {
 	const char* gple_version(void)
@@ -558,6 +586,20 @@ extern "C"
 		return predict_any(ctx, m, 1, Xq, Q, yq, pred_out, var_out, cutoff_out, err_out, derr_out);
 	}
 
+	int gple_validation_error(gple_ctx* ctx, const gple_model* m, const double* Xe, const double* ye, size_t M, double* error, double* grad)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(m != nullptr && Xe != nullptr && ye != nullptr && error != nullptr && M > 0, "gple_validation_error: null argument");
+				require(grad == nullptr || m->dv != nullptr, "gple_validation_error: the gradient needs a model trained with GPLE_CALC_DERIVATIVE");
+				validation_error(ctx, m, Xe, ye, M, error, grad);
+				return GPLE_OK;
+			}
+		);
+	}
+
 	int gple_loose_function(gple_ctx* ctx, const double* x, int nparam, double* grad, const double* X, const double* y, size_t N, const double* Xe, const double* ye, size_t M, double* value)
 	{
 		return guarded(
@@ -590,25 +632,11 @@ extern "C"
 					*value = std::nan("");
 					return rc;
 				}
-				const size_t w = nparam == 4 ? 1 : 2;
-				DeviceArray<double> xe(ctx, Xe, 2 * M, false), yc(ctx, ye, 2 * M, false);
-				// opt.cpp:451: the real kernel sees ExtraTrainingLabel.real()
-				double* yq = yc.dev;
-				if (nparam == 4)
-				{
-					yq = ctx->ws.get<double>("loose.yre", M);
-					GPLE_CUDA(cudaMemcpy2DAsync(yq, sizeof(double), yc.dev, 2 * sizeof(double), sizeof(double), M, cudaMemcpyDeviceToDevice, ctx->stream));
-				}
-				double* d_err = ctx->ws.get<double>("pred.err", 8);
-				double* d_cut = grad != nullptr ? ctx->ws.get<double>("pred.cut_tmp", w * M) : nullptr;
-				predict_device(ctx, m, xe.dev, M, yq, nullptr, nullptr, d_cut, d_err);
-				GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 128, d_err, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-				sync(ctx);
-				*value = trn_err + ctx->h_pinned[128];
+				double val_err = 0.0, vg[8];
+				validation_error(ctx, m, Xe, ye, M, &val_err, grad != nullptr ? vg : nullptr);
+				*value = trn_err + val_err;
 				if (grad != nullptr)
 				{
-					double vg[8];
-					validation_gradient(ctx, m, xe.dev, M, yq, d_cut, vg);
 					for (int p = 0; p < nparam; p++)
 					{
 						grad[p] = trn_grad[p] + vg[p];

@@ -19,7 +19,9 @@
 #include <complex>
 #include <future>
 #include <limits>
+#include <atomic>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <ostream>
 #include <stdexcept>
@@ -331,6 +333,83 @@ inline AllTrainingSets construct_training_sets(const AllPoints& density)
 	return result;
 }
 
+/// One trained element model per (training set, parameters).  NLopt evaluates the objective and the constraint callbacks of the
+/// constrained stages at the same parameters in turn (opt.cpp:594-617 / 644-719, 844-870 / 879-929), and each of them builds
+/// the element models from scratch; sharing the model halves the factorisations and derivative products of those stages.  An
+/// entry is keyed by the address of the element's training set (caller-owned and immutable during an optimisation,
+/// opt.cpp:538-545) and holds the last parameters seen; a request is a hit when the parameters are identical and the entry was
+/// trained with at least the requested quantities.  `clear()` at the start and end of an optimisation bounds its lifetime.
+class ModelCache
+{
+public:
+	static ModelCache& instance()
+	{
+		static ModelCache c;
+		return c;
+	}
+	std::shared_ptr<const TrainingKernel> real(const ElementTrainingSet& ts, const ParameterVector& theta, const bool err, const bool avg, const bool deriv)
+	{
+		return get<TrainingKernel>(Real, ts, theta, err, avg, deriv);
+	}
+	std::shared_ptr<const TrainingComplexKernel> complex(const ElementTrainingSet& ts, const ParameterVector& theta, const bool err, const bool avg, const bool deriv)
+	{
+		return get<TrainingComplexKernel>(Complex, ts, theta, err, avg, deriv);
+	}
+	void clear()
+	{
+		const std::lock_guard<std::mutex> lock(Mutex);
+		Real.clear();
+		Complex.clear();
+	}
+	std::size_t hits() const { return Hits; }
+	std::size_t misses() const { return Misses; }
+
+private:
+	template <typename K>
+	struct Entry
+	{
+		const ElementTrainingSet* key;
+		ParameterVector theta;
+		unsigned flags;
+		std::shared_ptr<const K> model;
+	};
+	std::mutex Mutex;
+	std::vector<Entry<TrainingKernel>> Real;
+	std::vector<Entry<TrainingComplexKernel>> Complex;
+	std::atomic<std::size_t> Hits{0}, Misses{0};
+
+	template <typename K>
+	std::shared_ptr<const K> get(std::vector<Entry<K>>& entries, const ElementTrainingSet& ts, const ParameterVector& theta, const bool err, const bool avg, const bool deriv)
+	{
+		const unsigned want = (err ? 1u : 0u) | (avg ? 2u : 0u) | (deriv ? 4u : 0u);
+		{
+			const std::lock_guard<std::mutex> lock(Mutex);
+			for (const auto& e : entries)
+			{
+				if (e.key == &ts && e.theta == theta && (e.flags & want) == want)
+				{
+					Hits++;
+					return e.model;
+				}
+			}
+		}
+		Misses++;
+		// the same element is never evaluated by two threads at once, so training happens outside the lock
+		auto model = std::make_shared<const K>(theta, ts, err, avg, deriv);
+		const std::lock_guard<std::mutex> lock(Mutex);
+		for (auto& e : entries)
+		{
+			if (e.key == &ts)
+			{
+				e = Entry<K>{&ts, theta, want, model};
+				return model;
+			}
+		}
+		entries.push_back(Entry<K>{&ts, theta, want, model});
+		return model;
+	}
+};
+
 /// gple/predict.h:89-143 -- the (up to) three element models of one time step; the three factorisations run concurrently
 class TrainingKernels
 {
@@ -339,7 +418,7 @@ public:
 	using QuantumVectorD = std::array<double, NumPES>;
 
 	/// gple/predict.cpp:362-388; an element stays nullopt when its training set is empty or all its parameters are 0 (:339-357)
-	TrainingKernels(const std::array<ParameterVector, NumElements>& ParameterVectors, const AllTrainingSets& TrainingSets, bool IsToCalculateError, bool IsToCalculateAverage, bool IsToCalculateDerivative)
+	TrainingKernels(const std::array<ParameterVector, NumElements>& ParameterVectors, const AllTrainingSets& TrainingSets, bool IsToCalculateError, bool IsToCalculateAverage, bool IsToCalculateDerivative, ModelCache* Cache = nullptr)
 	{
 		for_each_element_concurrently(
 			[&](const std::size_t e)
@@ -351,11 +430,13 @@ public:
 				}
 				if (e == 1)
 				{
-					OffDiagonal.emplace(ParameterVectors[e], TrainingSets[e], IsToCalculateError, IsToCalculateAverage, IsToCalculateDerivative);
+					OffDiagonal = Cache != nullptr ? Cache->complex(TrainingSets[e], ParameterVectors[e], IsToCalculateError, IsToCalculateAverage, IsToCalculateDerivative)
+												   : std::make_shared<const TrainingComplexKernel>(ParameterVectors[e], TrainingSets[e], IsToCalculateError, IsToCalculateAverage, IsToCalculateDerivative);
 				}
 				else
 				{
-					Diagonal[e / 2].emplace(ParameterVectors[e], TrainingSets[e], IsToCalculateError, IsToCalculateAverage, IsToCalculateDerivative);
+					Diagonal[e / 2] = Cache != nullptr ? Cache->real(TrainingSets[e], ParameterVectors[e], IsToCalculateError, IsToCalculateAverage, IsToCalculateDerivative)
+													   : std::make_shared<const TrainingKernel>(ParameterVectors[e], TrainingSets[e], IsToCalculateError, IsToCalculateAverage, IsToCalculateDerivative);
 				}
 			}
 		);
@@ -462,8 +543,9 @@ public:
 		}
 		return Diagonal[element / 2] ? Diagonal[element / 2]->handle() : nullptr;
 	}
-	std::array<std::optional<TrainingKernel>, NumPES> Diagonal;
-	std::optional<TrainingComplexKernel> OffDiagonal;
+	/// empty = the reference's std::nullopt (element not populated); shared so that a ModelCache can serve the same model twice
+	std::array<std::shared_ptr<const TrainingKernel>, NumPES> Diagonal;
+	std::shared_ptr<const TrainingComplexKernel> OffDiagonal;
 };
 
 /// gple/evolve.h:16-21 with the GPR-backed predict_distribution of gple/main.cpp:75-101

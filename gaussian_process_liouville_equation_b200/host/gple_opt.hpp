@@ -77,20 +77,51 @@ using ElementTrainingParameters = std::tuple<const ElementTrainingSet&, const El
 using AnalyticalLooseFunctionParameters = std::tuple<const AllTrainingSets&, const AllTrainingSets&>;					   // opt.cpp:589
 using AnalyticalConstraintParameters = std::tuple<const AllTrainingSets&, const QuantumVectorD&, const double&, const double&>; // opt.cpp:638
 
-/// loose_function (gple/opt.cpp:441-482): LOOCV error of the training set + squared error on the extra set
+/// loose_function (gple/opt.cpp:441-482): LOOCV error of the training set + squared error on the extra set.  Written like the
+/// reference's body -- a TrainingKernel on the training set, then the prediction error on the extra set -- with the trained model
+/// taken from the ModelCache (the averages are computed along, so that the constraint callback evaluated at the same x reuses it).
 inline double loose_function(const ParameterVector& x, ParameterVector& grad, void* params)
 {
 	const auto& [ts, ets] = *static_cast<ElementTrainingParameters*>(params);
-	double value = 0.0;
-	const int rc = gple_loose_function(
-		Context::get(), x.data(), int(x.size()), grad.empty() ? nullptr : grad.data(), std::get<0>(ts).data(), reinterpret_cast<const double*>(std::get<1>(ts).data()), std::get<0>(ts).cols(),
-		std::get<0>(ets).data(), reinterpret_cast<const double*>(std::get<1>(ets).data()), std::get<0>(ets).cols(), &value
-	);
-	Context::check(rc, "loose_function", true);
-	if (rc == GPLE_ERR_NOT_SPD)
+	const bool deriv = !grad.empty();
+	const std::size_t M = std::get<0>(ets).cols();
+	double value = std::numeric_limits<double>::quiet_NaN(), val = 0.0;
+	ParameterVector vg(grad.size(), 0.0);
+	auto validate = [&](const gple_model* m)
 	{
-		value = std::numeric_limits<double>::quiet_NaN();
-		std::fill(grad.begin(), grad.end(), std::numeric_limits<double>::quiet_NaN());
+		Context::check(gple_validation_error(Context::get(), m, std::get<0>(ets).data(), reinterpret_cast<const double*>(std::get<1>(ets).data()), M, &val, deriv ? vg.data() : nullptr), "loose_function");
+	};
+	if (x.size() == TrainingKernel::NumTotalParameters)
+	{
+		const auto k = ModelCache::instance().real(ts, x, true, true, deriv);
+		if (k->status() == GPLE_OK)
+		{
+			validate(k->handle());
+			value = k->get_error() + val;
+			const auto d = k->get_error_derivative();
+			for (std::size_t p = 0; p < grad.size(); p++)
+			{
+				grad[p] = d[p] + vg[p];
+			}
+		}
+	}
+	else
+	{
+		const auto k = ModelCache::instance().complex(ts, x, true, true, deriv);
+		if (k->status() == GPLE_OK)
+		{
+			validate(k->handle());
+			value = k->get_error() + val;
+			const auto d = k->get_error_derivative();
+			for (std::size_t p = 0; p < grad.size(); p++)
+			{
+				grad[p] = d[p] + vg[p];
+			}
+		}
+	}
+	if (!(value == value))
+	{
+		std::fill(grad.begin(), grad.end(), std::numeric_limits<double>::quiet_NaN()); // not positive definite: opt.cpp:476-480
 	}
 	make_normal(value);
 	for (double& g : grad)
@@ -169,7 +200,7 @@ inline void diagonal_constraints(const unsigned m, double* result, const unsigne
 	assert(n == 8 && (m == 2 || m == 3));
 	// construct_all_parameters_from_diagonal (opt.cpp:622-636): the off-diagonal element is absent (all-zero parameters)
 	const AllParameters all{ParameterVector(x, x + 4), ParameterVector(8, 0.0), ParameterVector(x + 4, x + 8)};
-	const TrainingKernels k(all, ts, false, true, grad != nullptr);
+	const TrainingKernels k(all, ts, true, true, grad != nullptr, &ModelCache::instance());
 	result[0] = k.calculate_population() - 1.0;
 	result[1] = k.calculate_total_energy_average(Energies) - TotalEnergy;
 	if (m == 3)
@@ -203,7 +234,7 @@ inline void full_constraints(const unsigned m, double* result, const unsigned n,
 	const auto& [ts, Energies, TotalEnergy, Purity] = *static_cast<AnalyticalConstraintParameters*>(params);
 	assert(n == 16 && m == 3);
 	const AllParameters all{ParameterVector(x, x + 4), ParameterVector(x + 4, x + 12), ParameterVector(x + 12, x + 16)};
-	const TrainingKernels k(all, ts, false, true, grad != nullptr);
+	const TrainingKernels k(all, ts, true, true, grad != nullptr, &ModelCache::instance());
 	result[0] = k.calculate_population() - 1.0;
 	result[1] = k.calculate_total_energy_average(Energies) - TotalEnergy;
 	result[2] = k.calculate_purity() - Purity;
@@ -340,6 +371,12 @@ public:
 	Result optimize(const AllPoints& density, const AllPoints& extra_points)
 	{
 		const AllTrainingSets TrainingSets = construct_training_sets(density), ExtraTrainingSets = construct_training_sets(extra_points);
+		// the cache is keyed by the addresses of these training sets: nothing cached may outlive them
+		ModelCache::instance().clear();
+		struct CacheGuard
+		{
+			~CacheGuard() { ModelCache::instance().clear(); }
+		} cache_guard;
 		const QuantumVectorD Energies = calculate_total_energy_average_each_surface(density, mass, pes_model);
 		// opt.cpp:1026-1052: bounds of the characteristic lengths from the spread of the current points
 		std::array<Bounds, NumElements> ParameterBounds;

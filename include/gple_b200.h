@@ -162,6 +162,10 @@ extern "C"
 	/* Replaces loose_function (gple/opt.cpp:441-482): LOOCV error of the training set + squared error on the
 	 * extra set (+ gradient when grad != NULL).  nparam = 4 (real kernel) or 8 (complex kernel).  The value is
 	 * returned un-clamped; the caller applies make_normal. */
+	/* The validation half of loose_function on an ALREADY trained model (opt.cpp:455-470): *error = |K* v - s y_e|^2 over the M extra
+	 * points; grad (4 / 8 doubles, or NULL) its parameter gradient (model trained with GPLE_CALC_DERIVATIVE).  Lets the host share
+	 * one trained model between the objective and the constraint callbacks that NLopt evaluates at the same parameters. */
+	int gple_validation_error(gple_ctx* ctx, const gple_model* model, const double* Xe, const double* ye, size_t M, double* error, double* grad);
 	int gple_loose_function(gple_ctx* ctx, const double* x, int nparam, double* grad, const double* X, const double* y, size_t N, const double* Xe, const double* ye, size_t M, double* value);
 
 	/* ---- dynamics ------------------------------------------------------------------------------------
