@@ -104,3 +104,15 @@ def loose_function(x, TrainingSet, ExtraTrainingSet, grad: bool = False, ctx=Non
         g = np.where(np.isfinite(g), g, big)
         return v, g
     return v
+
+
+def validation_error(kernel, ExtraTrainingSet, grad: bool = False, ctx=None):
+    """The validation half of loose_function (opt.cpp:455-470) on an already trained model: (error[, gradient])."""
+    import ctypes as C
+
+    ctx = ctx or L.default_context()
+    Xe, ye = L.f64(ExtraTrainingSet[0]), L.c128(ExtraTrainingSet[1])
+    err = C.c_double()
+    g = np.empty(len(kernel.get_parameters())) if grad else None
+    ctx.check(ctx.lib.gple_validation_error(ctx.h, kernel.h, L.addr(Xe), L.addr(ye), len(Xe), C.byref(err), L.addr(g)))
+    return (err.value, g) if grad else err.value

@@ -93,6 +93,8 @@ def test_gradients_parity(ck, oracle):
     vo, go = oracle.loose_function(THETA, X, y, Xq, yq, grad=True)
     assert val == pytest.approx(vo, rel=1e-8)
     assert np.abs(g - go).max() <= 1e-6 * np.abs(go).max()
+    ve, vg = dynamics.validation_error(k, (Xq, yq), grad=True)
+    assert k.get_error() + ve == pytest.approx(val, rel=1e-13) and np.abs(k.get_error_derivative() + vg - g).max() <= 1e-12 * np.abs(g).max()
 
 
 def test_nlml_objective_parity(ck, oracle):

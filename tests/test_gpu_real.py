@@ -125,6 +125,10 @@ def test_gradients_parity(gk, oracle):
     assert val == pytest.approx(vo, rel=1e-9)
     assert np.abs(g - go).max() <= 1e-7 * np.abs(go).max()
     assert dynamics.loose_function(th, (X, y), (Xq, yq)) == pytest.approx(vo, rel=1e-9)
+    # the same split the way the host shares a trained model between objective and constraints (gple_validation_error)
+    ve, vg = dynamics.validation_error(k, (Xq, yq), grad=True)
+    assert k.get_error() + ve == pytest.approx(val, rel=1e-13) and np.abs(k.get_error_derivative() + vg - g).max() <= 1e-12 * np.abs(g).max()
+    assert dynamics.validation_error(k, (Xq, yq)) == pytest.approx(ve, rel=1e-13)
 
 
 def test_large_n_properties(gk):
