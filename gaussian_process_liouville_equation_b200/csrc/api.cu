@@ -232,6 +232,19 @@ extern "C"
 				ctx->stream = ctx->own_stream;
 				ctx->h_pinned_count = 512;
 				GPLE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pinned), ctx->h_pinned_count * sizeof(double)));
+				// staging buffers of host-pointer arguments: a memory pool of this context's own, so that freed blocks are kept
+				// (the default pool returns them to the driver at every synchronisation) and are never recycled into another
+				// context's stream (which would chain the streams of concurrently working contexts together)
+				{
+					cudaMemPoolProps pp{};
+					pp.allocType = cudaMemAllocationTypePinned;
+					pp.handleTypes = cudaMemHandleTypeNone;
+					pp.location.type = cudaMemLocationTypeDevice;
+					pp.location.id = device;
+					GPLE_CUDA(cudaMemPoolCreate(&ctx->mempool, &pp));
+					unsigned long long threshold = ~0ull;
+					GPLE_CUDA(cudaMemPoolSetAttribute(ctx->mempool, cudaMemPoolAttrReleaseThreshold, &threshold));
+				}
 				cudaDeviceProp prop{};
 				GPLE_CUDA(cudaGetDeviceProperties(&prop, device));
 				ctx->num_sms = prop.multiProcessorCount;
@@ -262,6 +275,10 @@ extern "C"
 		if (ctx->h_pinned != nullptr)
 		{
 			cudaFreeHost(ctx->h_pinned);
+		}
+		if (ctx->mempool != nullptr)
+		{
+			cudaMemPoolDestroy(ctx->mempool);
 		}
 		if (ctx->aux_stream != nullptr)
 		{

@@ -126,6 +126,7 @@ struct gple_ctx
 	int device = 0;
 	cudaStream_t own_stream = nullptr;
 	// look-ahead of the factorisation: the bulk of a trailing update runs here while the next leaf runs on `stream`
+	cudaMemPool_t mempool = nullptr; // staging buffers of host-pointer arguments (DeviceArray)
 	cudaStream_t aux_stream = nullptr;
 	cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr;
 	cudaStream_t stream = nullptr;
@@ -182,7 +183,14 @@ struct DeviceArray
 			return;
 		}
 		host = const_cast<T*>(ptr);
-		GPLE_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dev), n * sizeof(T), ctx->stream));
+		if (ctx->mempool != nullptr)
+		{
+			GPLE_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&dev), n * sizeof(T), ctx->mempool, ctx->stream));
+		}
+		else
+		{
+			GPLE_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dev), n * sizeof(T), ctx->stream));
+		}
 		owned = true;
 		if (!is_output)
 		{
