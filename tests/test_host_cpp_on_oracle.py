@@ -117,3 +117,28 @@ def test_main_loop_logic():
     assert abs(pop0 - 1.0) < 0.15
     for pop, e, pur in ticks:
         assert abs(pop - pop0) < 0.05 and abs(e / e0 - 1.0) < 0.03 and abs(pur - pur0) < 0.15
+
+
+def test_cpp_optimiser_three_elements_logic(tmp_path):
+    """Diagonal and full constrained stages (diagonal_loose / full_loose, diagonal_constraints / full_constraints, the ModelCache
+    shared between them) with all three elements populated."""
+    from test_opt_cpp import write_points
+
+    exe = compile_on_mock(os.path.join(ROOT, "tests", "cpp", "opt_test.cpp"), "opt_test")
+    n, centre = 24, (0.0, syn.P0)
+    density, extra = [], []
+    for e in range(3):
+        X, y = syn.training_set(63, e, n, centre)
+        Xe, ye = syn.extra_points(63, e, X, 5 * n, centre)
+        density.append(syn.points_aos(X, y))
+        extra.append(syn.points_aos(Xe, ye))
+    o = [oracle_backend.observable_sums(1, density[e], syn.MASS, i) for i, e in enumerate((0, 2))]
+    e0 = 0.6 * o[0][7] / o[0][0] + 0.4 * o[1][7] / o[1][0]
+    path = os.path.join(tmp_path, "points.txt")
+    write_points(path, density, extra)
+    got = parse(subprocess.run([exe, path, "1", repr(syn.MASS), repr(e0), repr(syn.snapshot_purity()), "60", "150"], capture_output=True, text=True, check=True, timeout=900).stdout)
+    assert np.isfinite(got["error"]) and got["error"] >= 0.0
+    assert abs(got["population"] - 1.0) < 0.2 and abs(got["energy"] / e0 - 1.0) < 0.2
+    for e, npar in enumerate((4, 8, 4)):
+        assert all(np.isfinite(got[f"theta{e}_{p}"]) for p in range(npar))
+    assert got["steps0"] > 0 and got["steps1"] > 0 and got["steps2"] > 0 and got["steps3"] > 0 and got["steps4"] > 0
