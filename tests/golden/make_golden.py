@@ -1,4 +1,5 @@
-"""Generates tests/golden/gple_golden_v1.npz from the CPU oracle on seeded synthetic inputs.
+"""Generates tests/golden/gple_golden_v1.npz and gple_golden_v2.npz (NLML objective, Metropolis chains) from the CPU oracle on seeded
+synthetic inputs.
 
 The reference ships no golden vectors and cannot be built here, so these fixtures are
 oracle outputs; they freeze the oracle (any later change to oracle/ must reproduce them) and give the GPU
@@ -52,5 +53,33 @@ def main():
     print("wrote", len(out), "arrays")
 
 
+def main_v2():
+    """v2: the rows added after v1 -- NLML / LLT objective and Metropolis chains on the v1 element models."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "gple_golden_v1.npz"))
+    out = {}
+    k0 = orc.TrainingKernel(g["theta_r"], g["X0"], g["y0"], True, True, True)
+    k1 = orc.TrainingComplexKernel(g["theta_c"], g["X1"], g["y1"], True, True, True)
+    k2 = orc.TrainingKernel(g["theta_r"], g["X2"], g["y2"], True, True, False)
+    v, gr = k0.nlml(grad=True)
+    out.update(r_nlml=np.array(v), r_dnlml=gr)
+    v, gr = k1.nlml(grad=True)
+    out.update(c_nlml=np.array(v), c_dnlml=gr)
+    analytic = [syn.X0, syn.P0, syn.SIGMA_X, syn.SIGMA_P, 0.8, 0.6, 0.0, 0.4]
+    rng = syn.rng(41, 0)
+    start = np.zeros((32, 4))
+    start[:, 0] = syn.X0 + syn.SIGMA_X * rng.standard_normal(32)
+    start[:, 1] = syn.P0 + syn.SIGMA_P * rng.standard_normal(32)
+    pts, acc, chains = orc.markov_chains(start, 50, 0.5, 17, 5, 1, 0, analytic=analytic, want_chain=True)
+    out.update(mc_start=start, mc_analytic=np.array(analytic), mc_a_pts=pts, mc_a_accept=acc, mc_a_autocor=orc.chain_autocorrelation(chains))
+    centre_pts = np.column_stack([g["X0"][:32], np.zeros((32, 2))])
+    pts, acc, _ = orc.markov_chains(centre_pts, 20, 0.3, 17, 6, 0, 0, k00=k0, k10=k1, k11=k2)
+    out.update(mc_p_start=centre_pts, mc_p_pts=pts, mc_p_accept=acc)
+    out["philox"] = np.array([orc.philox_draws(17, 5, c, s) for c in range(3) for s in range(3)])
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "gple_golden_v2.npz"), **out)
+    print("wrote", len(out), "arrays (v2)")
+
+
 if __name__ == "__main__":
-    main()
+    if "--v2-only" not in sys.argv:
+        main()
+    main_v2()

@@ -63,3 +63,43 @@ def test_gpu_matches_golden():
         E, F, D = dynamics.adiabatic_pes(model, np.linspace(-6, 6, 25))
         assert close(np.hstack([E, F, D[:, None]]), G[f"pes_m{model}"], 1e-12)
     assert close(dynamics.observable_sums(1, pts[2], 2000.0, 1), G["obs"], 1e-12)
+
+
+G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gple_golden_v2.npz"))
+
+
+def test_oracle_reproduces_golden_v2(oracle):
+    """NLML objective and Metropolis chains (tests/golden/make_golden.py::main_v2)"""
+    k0 = oracle.TrainingKernel(G["theta_r"], G["X0"], G["y0"], True, True, True)
+    k1 = oracle.TrainingComplexKernel(G["theta_c"], G["X1"], G["y1"], True, True, True)
+    k2 = oracle.TrainingKernel(G["theta_r"], G["X2"], G["y2"], True, True, False)
+    v, g = k0.nlml(grad=True)
+    assert v == pytest.approx(float(G2["r_nlml"]), rel=1e-12) and close(g, G2["r_dnlml"], 1e-9)
+    v, g = k1.nlml(grad=True)
+    assert v == pytest.approx(float(G2["c_nlml"]), rel=1e-11) and close(g, G2["c_dnlml"], 1e-8)
+    pts, acc, chains = oracle.markov_chains(G2["mc_start"], 50, 0.5, 17, 5, 1, 0, analytic=list(G2["mc_analytic"]), want_chain=True)
+    assert np.array_equal(acc, G2["mc_a_accept"]) and close(pts, G2["mc_a_pts"], 1e-14) and close(oracle.chain_autocorrelation(chains), G2["mc_a_autocor"], 1e-12)
+    pts, acc, _ = oracle.markov_chains(G2["mc_p_start"], 20, 0.3, 17, 6, 0, 0, k00=k0, k10=k1, k11=k2)
+    assert np.array_equal(acc, G2["mc_p_accept"]) and close(pts, G2["mc_p_pts"], 1e-12)
+    assert np.array_equal(np.array([oracle.philox_draws(17, 5, c, s) for c in range(3) for s in range(3)]), G2["philox"])
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden_v2():
+    from gaussian_process_liouville_equation_b200 import complex_kernel, kernel, mc
+
+    k0 = kernel.TrainingKernel(G["theta_r"], (G["X0"], G["y0"]), True, True, True)
+    k1 = complex_kernel.TrainingComplexKernel(G["theta_c"], (G["X1"], G["y1"]), True, True, True)
+    k2 = kernel.TrainingKernel(G["theta_r"], (G["X2"], G["y2"]), True, True, False)
+    v, g = k0.get_negative_log_marginal_likelihood(grad=True)
+    assert v == pytest.approx(float(G2["r_nlml"]), rel=1e-9) and close(g, G2["r_dnlml"], 1e-7)
+    v, g = k1.get_negative_log_marginal_likelihood(grad=True)
+    assert v == pytest.approx(float(G2["c_nlml"]), rel=1e-9) and close(g, G2["c_dnlml"], 1e-7)
+    a = G2["mc_analytic"]
+    s = mc.Sampler(17, analytic=((a[0], a[1]), (a[2], a[3]), (a[4], a[5]), (a[6], a[7])))
+    pts, acc, chains = s.chains(G2["mc_start"], 50, 0.5, 1, 0, want_chain=True, stream=5)
+    assert np.array_equal(acc, G2["mc_a_accept"]) and close(pts, G2["mc_a_pts"], 1e-13) and close(s.autocorrelation(chains), G2["mc_a_autocor"], 1e-11)
+    s = mc.Sampler(17, kernels=[k0, k1, k2])
+    pts, acc, _ = s.chains(G2["mc_p_start"], 20, 0.3, 0, 0, stream=6)
+    same = np.all(np.abs(pts[:, :2] - G2["mc_p_pts"][:, :2]) <= 1e-12 * np.abs(G2["mc_p_pts"][:, :2]).max(), axis=1)
+    assert same.mean() >= 0.9 and np.array_equal(acc[same], G2["mc_p_accept"][same])
