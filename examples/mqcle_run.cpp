@@ -48,7 +48,8 @@ int main(int argc, char** argv)
 	Optimization::Result opt_result = optimizer.optimize(density, extra_points);
 	std::unique_ptr<TrainingKernels> all_kernels = std::make_unique<TrainingKernels>(optimizer.get_parameters(), density);
 	std::size_t optimisations = 1;
-	double t_opt = 0.0, t_evolve = 0.0, t_rebuild = 0.0, t_select = 0.0;
+	double t_opt = 0.0, t_evolve = 0.0, t_rebuild = 0.0, t_select = 0.0, t_evolve_late = 0.0;
+	std::size_t late_ticks = 0;
 	auto now = []() { return std::chrono::steady_clock::now(); };
 	auto since = [](const std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
 	auto output = [&](const std::size_t tick)
@@ -68,6 +69,11 @@ int main(int argc, char** argv)
 		evolve(extra_points, mass, dt, *all_kernels, pes_model);
 		IsSmall = is_very_small(density, mass, dt, *all_kernels, pes_model);
 		t_evolve += since(t0);
+		if (2 * iTick > TotalTicks) // second half of the run: kernels loaded, workspaces grown, all elements settled
+		{
+			t_evolve_late += since(t0);
+			late_ticks++;
+		}
 		bool IsOptimized = false;
 		auto reoptimize = [&]()
 		{
@@ -107,6 +113,7 @@ int main(int argc, char** argv)
 	}
 	const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - begin).count();
 	std::printf("elements %zu %zu %zu\noptimisations %zu\nwall_s %.3f\n", density[0].size(), density[1].size(), density[2].size(), optimisations, wall);
+	std::printf("seconds_evolve_second_half %.4f\nticks_second_half %zu\n", t_evolve_late, late_ticks);
 	std::printf("seconds_evolve %.4f\nseconds_rebuild %.4f\nseconds_optimise_in_loop %.4f\nseconds_new_element_selection %.4f\n", t_evolve, t_rebuild, t_opt, t_select);
 	return 0;
 }
