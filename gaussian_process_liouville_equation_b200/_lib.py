@@ -54,6 +54,7 @@ SIGNATURES = {
     "gple_last_error": (C.c_char_p, [_vp]),
     "gple_launch_count": (C.c_ulonglong, [_vp]),
     "gple_kernel_real": (C.c_int, [_vp, _dp, _sz, _dp, _sz, _dp, C.c_int, _dp, _dp]),
+    "gple_kernel_complex_derivatives": (C.c_int, [_vp, _dp, _sz, _dp, _sz, _dp, C.c_int, _dp, _dp]),
     "gple_kernel_complex": (C.c_int, [_vp, _dp, _sz, _dp, _sz, _dp, C.c_int, _dp, _dp]),
     "gple_train_real": (C.c_int, [_vp, _dp, _dp, _sz, _dp, C.c_uint, C.POINTER(_vp), C.POINTER(RealScalars)]),
     "gple_train_complex": (C.c_int, [_vp, _dp, _dp, _sz, _dp, C.c_uint, C.POINTER(_vp), C.POINTER(ComplexScalars)]),

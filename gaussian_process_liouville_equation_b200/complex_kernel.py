@@ -25,6 +25,17 @@ def kernel_matrices(left_feature, right_feature, parameter, same_set: bool, ctx=
     return K.T, Kt.T
 
 
+def kernel_derivatives(left_feature, right_feature, parameter, same_set: bool, ctx=None):
+    """calculate_derivative / calculate_pseudo_derivative (complex_kernel.cpp:20-59, 74-132): dK (8, nL, nR) real, dKt (8, nL, nR) complex."""
+    ctx = ctx or L.default_context()
+    XL, XR, th = L.f64(left_feature), L.f64(right_feature), L.f64(parameter)
+    nL, nR = len(XL), len(XR)
+    dK = np.empty((8, nR, nL))
+    dKt = np.empty((8, nR, nL), dtype=np.complex128)
+    ctx.check(ctx.lib.gple_kernel_complex_derivatives(ctx.h, L.addr(XL), nL, L.addr(XR), nR, L.addr(th), int(same_set), L.addr(dK), L.addr(dKt)))
+    return dK.transpose(0, 2, 1), dKt.transpose(0, 2, 1)
+
+
 class TrainingComplexKernel:
     def __init__(self, Parameter, TrainingSet, IsToCalculateError=True, IsToCalculateAverage=True, IsToCalculateDerivative=False, ctx=None):
         self.ctx = ctx or L.default_context()

@@ -398,6 +398,23 @@ extern "C"
 		);
 	}
 
+	int gple_kernel_complex_derivatives(gple_ctx* ctx, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[8], int same_set, double* dK_out, double* dKt_out)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(XL != nullptr && XR != nullptr && theta != nullptr && (dK_out != nullptr || dKt_out != nullptr) && nL > 0 && nR > 0, "gple_kernel_complex_derivatives: null argument or empty set");
+				DeviceArray<double> l(ctx, XL, 2 * nL, false), r(ctx, XR, 2 * nR, false), k(ctx, dK_out, 8 * nL * nR, true), kt(ctx, dKt_out, 16 * nL * nR, true);
+				kernel_complex_derivatives_device(ctx, l.dev, int(nL), r.dev, int(nR), theta, same_set, k.dev, kt.dev);
+				k.finish();
+				kt.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+
 	int gple_train_real(gple_ctx* ctx, const double* X, const double* y, size_t N, const double theta[4], unsigned flags, gple_model** model, gple_real_scalars* out)
 	{
 		return guarded(

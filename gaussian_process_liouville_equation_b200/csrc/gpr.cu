@@ -997,6 +997,60 @@ __global__ void __launch_bounds__(256) kernel_complex_kernel(const double2* __re
 	Kt[o] = make_double2(mag2 * (kr - ki), mag2 * (2.0 * kc));
 }
 
+/// calculate_derivative / calculate_pseudo_derivative of the complex kernel (complex_kernel.cpp:20-59, 74-132), materialised:
+/// dK[p] (real) and dKt[p] (complex), p = sigma, sigma_R, l_Rx, l_Rp, sigma_I, l_Ix, l_Ip, sigma_n, column-major nL x nR each.
+/// As in the reference the sub-kernel blocks carry NO sigma^2 and the noise entry is 2 sigma_n on the diagonal of a same-set
+/// matrix (quirk q2); the correlation kernel's parameters are functions of the R / I ones (chain rule, :96-126).
+struct ComplexDerivSpec
+{
+	double sigma, noise, sr, si, lr[2], li[2], lc[2];
+};
+__global__ void __launch_bounds__(256) kernel_complex_deriv_kernel(const double2* __restrict__ XL, const int nL, const double2* __restrict__ XR, const int nR, const GaussBlock gr, const GaussBlock gi, const GaussBlock gc, const ComplexDerivSpec sp, const int same, double* __restrict__ dK, double2* __restrict__ dKt)
+{
+	const int r = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+	if (r >= nL)
+	{
+		return;
+	}
+	const double2 a = XL[r], b = XR[c];
+	const double kr = gauss_value(gr, a, b), ki = gauss_value(gi, a, b), kc = gauss_value(gc, a, b);
+	const double delta = same ? (r == c ? 1.0 : 0.0) : ((a.x == b.x && a.y == b.y) ? 1.0 : 0.0);
+	const double d2[2] = {(a.x - b.x) * (a.x - b.x), (a.y - b.y) * (a.y - b.y)};
+	const size_t plane = size_t(nL) * nR, o = size_t(c) * nL + r;
+	const double m2 = sp.sigma * sp.sigma;
+	double D[8];
+	double2 Dt[8];
+	D[0] = 2.0 / sp.sigma * (m2 * (kr + ki + sp.noise * sp.noise * delta));
+	Dt[0] = make_double2(2.0 / sp.sigma * (m2 * (kr - ki)), 2.0 / sp.sigma * (m2 * (2.0 * kc)));
+	D[1] = 2.0 / sp.sr * kr;
+	D[4] = 2.0 / sp.si * ki;
+	Dt[1] = make_double2(D[1], 2.0 / sp.sr * kc);
+	Dt[4] = make_double2(-D[4], 2.0 / sp.si * kc);
+#pragma unroll
+	for (int d = 0; d < 2; d++)
+	{
+		const double dc = kc * d2[d] / (sp.lc[d] * sp.lc[d] * sp.lc[d]); // derivative of the correlation kernel over its own length
+		D[2 + d] = kr * d2[d] / (sp.lr[d] * sp.lr[d] * sp.lr[d]);
+		D[5 + d] = ki * d2[d] / (sp.li[d] * sp.li[d] * sp.li[d]);
+		Dt[2 + d] = make_double2(D[2 + d], 2.0 * (1.0 / sp.lr[d] - sp.lr[d] / (sp.lc[d] * sp.lc[d])) * kc + sp.lr[d] / sp.lc[d] * dc);
+		Dt[5 + d] = make_double2(-D[5 + d], 2.0 * (1.0 / sp.li[d] - sp.li[d] / (sp.lc[d] * sp.lc[d])) * kc + sp.li[d] / sp.lc[d] * dc);
+	}
+	D[7] = (same && r == c) ? 2.0 * sp.noise : 0.0;
+	Dt[7] = make_double2(0.0, 0.0);
+#pragma unroll
+	for (int p = 0; p < 8; p++)
+	{
+		if (dK != nullptr)
+		{
+			dK[p * plane + o] = D[p];
+		}
+		if (dKt != nullptr)
+		{
+			dKt[p * plane + o] = Dt[p];
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host-side orchestration
 // ---------------------------------------------------------------------------------------------------
@@ -1526,6 +1580,14 @@ void kernel_complex_device(gple_ctx* ctx, const double* XL, int nL, const double
 	const ComplexSub c = complex_sub(th);
 	const GaussBlock gr{c.sr * c.sr, 1.0 / c.lr[0], 1.0 / c.lr[1], 0.0}, gi{c.si * c.si, 1.0 / c.li[0], 1.0 / c.li[1], 0.0}, gc{c.sc * c.sc, 1.0 / c.lc[0], 1.0 / c.lc[1], 0.0};
 	GPLE_LAUNCH(ctx, kernel_complex_kernel, dim3((nL + 255) / 256, nR), 256, 0, reinterpret_cast<const double2*>(XL), nL, reinterpret_cast<const double2*>(XR), nR, gr, gi, gc, th[0] * th[0], th[7] * th[7], same, K, reinterpret_cast<double2*>(Kt));
+}
+
+void kernel_complex_derivatives_device(gple_ctx* ctx, const double* XL, int nL, const double* XR, int nR, const double* th, int same, double* dK, double* dKt)
+{
+	const ComplexSub c = complex_sub(th);
+	const GaussBlock gr{c.sr * c.sr, 1.0 / c.lr[0], 1.0 / c.lr[1], 0.0}, gi{c.si * c.si, 1.0 / c.li[0], 1.0 / c.li[1], 0.0}, gc{c.sc * c.sc, 1.0 / c.lc[0], 1.0 / c.lc[1], 0.0};
+	const ComplexDerivSpec sp{th[0], th[7], c.sr, c.si, {c.lr[0], c.lr[1]}, {c.li[0], c.li[1]}, {c.lc[0], c.lc[1]}};
+	GPLE_LAUNCH(ctx, kernel_complex_deriv_kernel, dim3((nL + 255) / 256, nR), 256, 0, reinterpret_cast<const double2*>(XL), nL, reinterpret_cast<const double2*>(XR), nR, gr, gi, gc, sp, same, dK, reinterpret_cast<double2*>(dKt));
 }
 
 } // namespace gple

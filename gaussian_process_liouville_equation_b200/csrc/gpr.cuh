@@ -14,6 +14,7 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 int set_variance_gemm_variant(int variant);
 double bench_variance_gemm(gple_ctx* ctx, int variant, int rows, int n, int iters);
 void kernel_real_device(gple_ctx* ctx, const double* XL, int nL, const double* XR, int nR, const double* theta, int same, double* K, double* dK);
+void kernel_complex_derivatives_device(gple_ctx* ctx, const double* XL, int nL, const double* XR, int nR, const double* theta, int same, double* dK, double* dKt);
 void kernel_complex_device(gple_ctx* ctx, const double* XL, int nL, const double* XR, int nR, const double* theta, int same, double* K, double* Kt);
 
 /// gpr_deriv.cu: parameter gradients (kernel.cpp:337-477, 524-541; complex_kernel.cpp:379-590, 648-667)

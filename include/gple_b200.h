@@ -96,6 +96,11 @@ extern "C"
 	/* Replaces ComplexKernelBase::ComplexKernelBase (gple/complex_kernel.cpp:134-200).
 	 * theta = (sigma, sigma_R, l_Rx, l_Rp, sigma_I, l_Ix, l_Ip, sigma_n) (complex_kernel.cpp:230-256).
 	 * K_out: nL x nR real; Kt_out: nL x nR complex (pseudo-covariance). */
+	/* calculate_derivative / calculate_pseudo_derivative of the complex kernel (gple/complex_kernel.cpp:20-59, 74-132), materialised:
+	 * dK_out = 8 real nL x nR matrices, dKt_out = 8 complex ones (either may be NULL), parameter order sigma, sigma_R, l_Rx, l_Rp,
+	 * sigma_I, l_Ix, l_Ip, sigma_n, column-major.  The training path never stores them (it works in composite form); this entry
+	 * exists for the getters / parity with the reference's derivative arrays, quirk q2 included. */
+	int gple_kernel_complex_derivatives(gple_ctx* ctx, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[8], int same_set, double* dK_out, double* dKt_out);
 	int gple_kernel_complex(gple_ctx* ctx, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[8], int same_set, double* K_out, double* Kt_out);
 
 	/* ---- training ----------------------------------------------------------------------------------

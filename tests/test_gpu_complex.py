@@ -30,6 +30,12 @@ def test_kernel_matrices_parity(ck, oracle):
         Ko, Kto = oracle.kernel_complex(XL, XR, THETA, same, False)
         assert (np.abs(K - Ko) <= 1e-12 * np.abs(Ko) + 1e-300).all()
         assert (np.abs(Kt - Kto) <= 1e-12 * np.abs(Kto) + 1e-300).all()
+        # calculate_derivative / calculate_pseudo_derivative (complex_kernel.cpp:20-59, 74-132), incl. quirk q2
+        dK, dKt = ck.kernel_derivatives(XL, XR, THETA, same)
+        _, _, dKo, dKto = oracle.kernel_complex(XL, XR, THETA, same, True)
+        for p in range(8):
+            assert (np.abs(dK[p] - dKo[p]) <= 1e-12 * np.abs(dKo[p]) + 1e-14 * np.abs(dKo[p]).max() + 1e-300).all(), p
+            assert (np.abs(dKt[p] - dKto[p]) <= 1e-12 * np.abs(dKto[p]) + 1e-14 * np.abs(dKto[p]).max() + 1e-300).all(), p
 
 
 @pytest.mark.parametrize("n,theta", [(48, THETA), (200, THETA), (150, syn.theta_complex())])
