@@ -153,6 +153,125 @@ inline void make_normal(double& d)
 	}
 }
 
+/// Column-major dense matrix with the layout of the reference's Eigen::MatrixXd / MatrixXcd (Eigen is not available here)
+template <typename T>
+struct Matrix
+{
+	std::size_t Rows = 0, Cols = 0;
+	std::vector<T> d;
+	Matrix() = default;
+	Matrix(std::size_t r, std::size_t c): Rows(r), Cols(c), d(r * c) {}
+	std::size_t rows() const { return Rows; }
+	std::size_t cols() const { return Cols; }
+	T& operator()(std::size_t r, std::size_t c) { return d[c * Rows + r]; }
+	const T& operator()(std::size_t r, std::size_t c) const { return d[c * Rows + r]; }
+	T* data() { return d.data(); }
+	const T* data() const { return d.data(); }
+};
+using MatrixXd = Matrix<double>;
+using MatrixXcd = Matrix<std::complex<double>>;
+
+/// gple/kernel.h:29-106 -- kernel matrix of two point sets and, optionally, its derivatives over (sigma_f, l_x, l_p, sigma_n).
+/// As in the reference (kernel.cpp:217-242, :8-31) the two sets count as "the same set" when they are the same buffer.
+class KernelBase
+{
+public:
+	static constexpr std::size_t NumTotalParameters = 1 + PhaseDim + 1;
+	static constexpr double RescaleMaximum = 10.0;
+	using KernelParameter = std::tuple<double, ClassicalPhaseVector, double>; // magnitude, characteristic lengths, noise
+	template <typename T>
+	using ParameterArray = std::array<T, NumTotalParameters>;
+
+	KernelBase(const KernelParameter& Parameter, const PhasePoints& left_feature, const PhasePoints& right_feature, const bool IsToCalculateDerivative):
+		KernelParams(Parameter), LeftFeature(left_feature), RightFeature(right_feature), KernelMatrix(left_feature.cols(), right_feature.cols())
+	{
+		const auto& [mag, l, noise] = KernelParams;
+		const double theta[4] = {mag, l[0], l[1], noise};
+		const std::size_t nL = left_feature.cols(), nR = right_feature.cols();
+		std::vector<double> dk(IsToCalculateDerivative ? 4 * nL * nR : 0);
+		Context::check(gple_kernel_real(Context::get(), left_feature.data(), nL, right_feature.data(), nR, theta, left_feature.data() == right_feature.data() ? 1 : 0, KernelMatrix.data(), IsToCalculateDerivative ? dk.data() : nullptr), "KernelBase");
+		if (IsToCalculateDerivative)
+		{
+			Derivatives.emplace();
+			for (std::size_t p = 0; p < NumTotalParameters; p++)
+			{
+				(*Derivatives)[p] = MatrixXd(nL, nR);
+				std::copy(dk.cbegin() + p * nL * nR, dk.cbegin() + (p + 1) * nL * nR, (*Derivatives)[p].d.begin());
+			}
+		}
+	}
+	const KernelParameter& get_formatted_parameters() const { return KernelParams; }
+	const PhasePoints& get_left_feature() const { return LeftFeature; }
+	const PhasePoints& get_right_feature() const { return RightFeature; }
+	const MatrixXd& get_kernel() const { return KernelMatrix; }
+	const ParameterArray<MatrixXd>& get_derivative() const
+	{
+		assert(Derivatives.has_value());
+		return Derivatives.value();
+	}
+
+private:
+	const KernelParameter KernelParams;
+	const PhasePoints LeftFeature;
+	const PhasePoints RightFeature;
+	MatrixXd KernelMatrix;
+	std::optional<ParameterArray<MatrixXd>> Derivatives;
+};
+
+/// gple/complex_kernel.h:14-145 -- covariance K and pseudo-covariance K~ of the widely-linear complex process and their
+/// derivative arrays over (sigma, sigma_R, l_Rx, l_Rp, sigma_I, l_Ix, l_Ip, sigma_n) (complex_kernel.cpp:20-59, 74-132)
+class ComplexKernelBase
+{
+public:
+	static constexpr std::size_t NumTotalParameters = 1 + 2 * (1 + PhaseDim) + 1;
+	template <typename T>
+	using ParameterArray = std::array<T, NumTotalParameters>;
+
+	ComplexKernelBase(const ParameterVector& Parameter, const PhasePoints& left_feature, const PhasePoints& right_feature, const bool IsToCalculateDerivative):
+		Params(Parameter), KernelMatrix(left_feature.cols(), right_feature.cols()), PseudoKernelMatrix(left_feature.cols(), right_feature.cols())
+	{
+		assert(Parameter.size() == NumTotalParameters);
+		const std::size_t nL = left_feature.cols(), nR = right_feature.cols();
+		const int same = left_feature.data() == right_feature.data() ? 1 : 0;
+		Context::check(gple_kernel_complex(Context::get(), left_feature.data(), nL, right_feature.data(), nR, Params.data(), same, KernelMatrix.data(), reinterpret_cast<double*>(PseudoKernelMatrix.data())), "ComplexKernelBase");
+		if (IsToCalculateDerivative)
+		{
+			std::vector<double> dk(8 * nL * nR);
+			std::vector<std::complex<double>> dkt(8 * nL * nR);
+			Context::check(gple_kernel_complex_derivatives(Context::get(), left_feature.data(), nL, right_feature.data(), nR, Params.data(), same, dk.data(), reinterpret_cast<double*>(dkt.data())), "ComplexKernelBase derivatives");
+			Derivatives.emplace();
+			PseudoDerivatives.emplace();
+			for (std::size_t p = 0; p < NumTotalParameters; p++)
+			{
+				(*Derivatives)[p] = MatrixXd(nL, nR);
+				(*PseudoDerivatives)[p] = MatrixXcd(nL, nR);
+				std::copy(dk.cbegin() + p * nL * nR, dk.cbegin() + (p + 1) * nL * nR, (*Derivatives)[p].d.begin());
+				std::copy(dkt.cbegin() + p * nL * nR, dkt.cbegin() + (p + 1) * nL * nR, (*PseudoDerivatives)[p].d.begin());
+			}
+		}
+	}
+	const ParameterVector& get_parameters() const { return Params; }
+	const MatrixXd& get_kernel() const { return KernelMatrix; }
+	const MatrixXcd& get_pseudo_kernel() const { return PseudoKernelMatrix; }
+	const ParameterArray<MatrixXd>& get_derivatives() const
+	{
+		assert(Derivatives.has_value());
+		return Derivatives.value();
+	}
+	const ParameterArray<MatrixXcd>& get_pseudo_derivatives() const
+	{
+		assert(PseudoDerivatives.has_value());
+		return PseudoDerivatives.value();
+	}
+
+private:
+	const ParameterVector Params;
+	MatrixXd KernelMatrix;
+	MatrixXcd PseudoKernelMatrix;
+	std::optional<ParameterArray<MatrixXd>> Derivatives;
+	std::optional<ParameterArray<MatrixXcd>> PseudoDerivatives;
+};
+
 /// gple/kernel.h:111-280
 class TrainingKernel
 {

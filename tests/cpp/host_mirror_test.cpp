@@ -32,6 +32,19 @@ int main(int argc, char** argv)
 		}
 	}
 	const ParameterVector tr{1.0, sx, sp, 1e-2}, tc{1.0, 1.2, 0.8 * sx, 1.1 * sp, 0.7, 1.1 * sx, 0.9 * sp, 2e-2};
+	{
+		// gple/kernel.h:29-106, complex_kernel.h:14-145: kernel matrices and their derivative arrays of the first 12 points
+		PhasePoints f(12);
+		for (std::size_t i = 0; i < 12; i++)
+		{
+			f(0, i) = density[0][i].r[0];
+			f(1, i) = density[0][i].r[1];
+		}
+		const KernelBase kb({1.0, {sx, sp}, 1e-2}, f, f, true);
+		std::printf("kb_K_3_5 %.17g\nkb_K_4_4 %.17g\nkb_dK1_3_5 %.17g\nkb_dK3_4_4 %.17g\n", kb.get_kernel()(3, 5), kb.get_kernel()(4, 4), kb.get_derivative()[1](3, 5), kb.get_derivative()[3](4, 4));
+		const ComplexKernelBase ckb({1.0, 1.2, 0.8 * sx, 1.1 * sp, 0.7, 1.1 * sx, 0.9 * sp, 2e-2}, f, f, true);
+		std::printf("ckb_Kt_3_5_im %.17g\nckb_dKt2_3_5_im %.17g\nckb_dK7_4_4 %.17g\n", ckb.get_pseudo_kernel()(3, 5).imag(), ckb.get_pseudo_derivatives()[2](3, 5).imag(), ckb.get_derivatives()[7](4, 4));
+	}
 	const TrainingKernels kernels({tr, tc, tr}, density);
 	std::printf("population %.17g\n", kernels.calculate_population());
 	std::printf("purity %.17g\n", kernels.calculate_purity());

@@ -61,6 +61,22 @@ extern "C"
 	unsigned long long gple_launch_count(const gple_ctx* ctx) { return ctx != nullptr ? ctx->calls : 0; }
 	const char* gple_version(void) { return "mock (CPU oracle) -- tests only"; }
 
+	int gple_kernel_real(gple_ctx*, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[4], int same_set, double* K_out, double* dK_out)
+	{
+		orc_kernel_real(XL, nL, XR, nR, theta, same_set, dK_out != nullptr, K_out, dK_out);
+		return GPLE_OK;
+	}
+	int gple_kernel_complex(gple_ctx*, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[8], int same_set, double* K_out, double* Kt_out)
+	{
+		orc_kernel_complex(XL, nL, XR, nR, theta, same_set, 0, K_out, Kt_out, nullptr, nullptr);
+		return GPLE_OK;
+	}
+	int gple_kernel_complex_derivatives(gple_ctx*, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[8], int same_set, double* dK_out, double* dKt_out)
+	{
+		std::vector<double> K(nL * nR), Kt(2 * nL * nR);
+		orc_kernel_complex(XL, nL, XR, nR, theta, same_set, 1, K.data(), Kt.data(), dK_out, dKt_out);
+		return GPLE_OK;
+	}
 	int gple_train_real(gple_ctx* ctx, const double* X, const double* y, size_t N, const double theta[4], unsigned flags, gple_model** model, gple_real_scalars* out)
 	{
 		if (X == nullptr || y == nullptr || N == 0 || model == nullptr)

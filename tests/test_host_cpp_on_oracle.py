@@ -55,6 +55,10 @@ def test_host_mirror_logic(tmp_path):
     k0, k1, k2 = orc.TrainingKernel(tr, X, ys[0]), orc.TrainingComplexKernel(tc, X, ys[1]), orc.TrainingKernel(tr, X, ys[2])
     # the aggregators of TrainingKernels (predict.cpp:395-463) on top of the same oracle numbers; the C++ side computes exp / pow
     # of the synthetic labels itself, so agreement is to rounding of those inputs, not bitwise
+    Kb, dKb = orc.kernel_real(X[:12], X[:12], tr, True, True)
+    _, Ktb, dKcb, dKtb = orc.kernel_complex(X[:12], X[:12], tc, True, True)
+    assert got["kb_K_3_5"] == pytest.approx(Kb[3, 5], rel=1e-12) and got["kb_dK1_3_5"] == pytest.approx(dKb[1][3, 5], rel=1e-11) and got["kb_dK3_4_4"] == pytest.approx(dKb[3][4, 4], rel=1e-12)
+    assert got["ckb_Kt_3_5_im"] == pytest.approx(Ktb[3, 5].imag, rel=1e-12) and got["ckb_dKt2_3_5_im"] == pytest.approx(dKtb[2][3, 5].imag, rel=1e-11) and got["ckb_dK7_4_4"] == pytest.approx(dKcb[7][4, 4], rel=1e-12)
     assert got["population"] == pytest.approx(k0.population + k2.population, rel=1e-10)
     assert got["purity"] == pytest.approx(k0.purity + k2.purity + 2 * k1.purity, rel=1e-10)
     assert got["error00"] == pytest.approx(k0.error, rel=1e-8) and got["error10"] == pytest.approx(k1.error, rel=1e-8)

@@ -36,6 +36,12 @@ def test_host_mirror_matches_oracle(oracle, tmp_path):
     tr = np.array([1.0, sx, sp, 1e-2])
     tc = np.array([1.0, 1.2, 0.8 * sx, 1.1 * sp, 0.7, 1.1 * sx, 0.9 * sp, 2e-2])
     k0, k1, k2 = oracle.TrainingKernel(tr, X, ys[0]), oracle.TrainingComplexKernel(tc, X, ys[1]), oracle.TrainingKernel(tr, X, ys[2])
+    Kb, dKb = oracle.kernel_real(X[:12], X[:12], tr, True, True)
+    _, Ktb, dKcb, dKtb = oracle.kernel_complex(X[:12], X[:12], tc, True, True)
+    assert got["kb_K_3_5"] == pytest.approx(Kb[3, 5], rel=1e-12) and got["kb_K_4_4"] == pytest.approx(Kb[4, 4], rel=1e-12)
+    assert got["kb_dK1_3_5"] == pytest.approx(dKb[1][3, 5], rel=1e-11) and got["kb_dK3_4_4"] == pytest.approx(dKb[3][4, 4], rel=1e-12)
+    assert got["ckb_Kt_3_5_im"] == pytest.approx(Ktb[3, 5].imag, rel=1e-12) and got["ckb_dKt2_3_5_im"] == pytest.approx(dKtb[2][3, 5].imag, rel=1e-11)
+    assert got["ckb_dK7_4_4"] == pytest.approx(dKcb[7][4, 4], rel=1e-12)
     assert got["population"] == pytest.approx(k0.population + k2.population, rel=1e-9)
     assert got["purity"] == pytest.approx(k0.purity + k2.purity + 2 * k1.purity, rel=1e-8)
     assert got["error00"] == pytest.approx(k0.error, rel=1e-8) and got["error10"] == pytest.approx(k1.error, rel=1e-7)
