@@ -146,3 +146,15 @@ def test_cpp_optimiser_three_elements_logic(tmp_path):
     for e, npar in enumerate((4, 8, 4)):
         assert all(np.isfinite(got[f"theta{e}_{p}"]) for p in range(npar))
     assert got["steps0"] > 0 and got["steps1"] > 0 and got["steps2"] > 0 and got["steps3"] > 0 and got["steps4"] > 0
+
+
+def test_main_loop_logic_at_the_crossing():
+    """Started at the crossing the run must populate rho10 and rho11: is_very_small, new_element_point_selection (Metropolis
+    tuning on the new_point_predict target, extra points) and the element-change re-optimisation of main.cpp:145-162."""
+    exe = compile_on_mock(os.path.join(ROOT, "examples", "mqcle_run.cpp"), "mqcle_run")
+    out = subprocess.run([exe, "16", "2", "0", "1", "7", "-0.3"], capture_output=True, text=True, check=True, timeout=900).stdout
+    ticks = [[float(v) for v in line.split()[2:]] for line in out.splitlines() if line.startswith("tick")]
+    info = {line.split()[0]: line.split()[1:] for line in out.splitlines() if not line.startswith("tick")}
+    assert len(ticks) == 3 and info["elements"] == ["16", "16", "16"] and int(info["optimisations"][0]) >= 2
+    for pop, e, pur in ticks:
+        assert 0.8 < pop < 1.2 and 0.8 < pur < 1.2
