@@ -114,8 +114,8 @@ def test_main_loop_logic():
     """examples/mqcle_run.cpp on the oracle: far from the crossing nothing but rho00 is populated and the averages are conserved."""
     exe = compile_on_mock(os.path.join(ROOT, "examples", "mqcle_run.cpp"), "mqcle_run")
     out = subprocess.run([exe, "32", "3", "0", "1", "7"], capture_output=True, text=True, check=True, timeout=900).stdout
-    ticks = [[float(v) for v in line.split()[2:]] for line in out.splitlines() if line.startswith("tick")]
-    info = {line.split()[0]: line.split()[1:] for line in out.splitlines() if not line.startswith("tick")}
+    ticks = [[float(v) for v in line.split()[2:]] for line in out.splitlines() if line.startswith("tick ")]
+    info = {line.split()[0]: line.split()[1:] for line in out.splitlines() if not line.startswith("tick ")}
     assert len(ticks) == 4 and info["elements"] == ["32", "0", "0"]
     pop0, e0, pur0 = ticks[0]
     assert abs(pop0 - 1.0) < 0.15
@@ -153,8 +153,8 @@ def test_main_loop_logic_at_the_crossing():
     tuning on the new_point_predict target, extra points) and the element-change re-optimisation of main.cpp:145-162."""
     exe = compile_on_mock(os.path.join(ROOT, "examples", "mqcle_run.cpp"), "mqcle_run")
     out = subprocess.run([exe, "16", "2", "0", "1", "7", "-0.3"], capture_output=True, text=True, check=True, timeout=900).stdout
-    ticks = [[float(v) for v in line.split()[2:]] for line in out.splitlines() if line.startswith("tick")]
-    info = {line.split()[0]: line.split()[1:] for line in out.splitlines() if not line.startswith("tick")}
+    ticks = [[float(v) for v in line.split()[2:]] for line in out.splitlines() if line.startswith("tick ")]
+    info = {line.split()[0]: line.split()[1:] for line in out.splitlines() if not line.startswith("tick ")}
     assert len(ticks) == 3 and info["elements"] == ["16", "16", "16"] and int(info["optimisations"][0]) >= 2
     for pop, e, pur in ticks:
         assert 0.8 < pop < 1.2 and 0.8 < pur < 1.2
