@@ -326,7 +326,7 @@ def run_ours(args):
                      "traffic_note": "ncu dram__bytes_read+write of a real-element launch (2.338 GB for 8.44e10 flops, profiles/r01_var_gemm_ncu_full.md), scaled by flops per launch",
                      "peak_source": "measured live by gple_measure_fp64_peak (register-resident DMMA.8x8x4 loop); MEASURED_PEAKS.json has no FP64 entry",
                      "launches": var_n, "avg_launch_ms": var_ms / max(var_n, 1), "share_of_step": var_ms / total_ms,
-                     "flops_counted": "executed (triangular) flops rows*n*(n+128); the reference formulation K* K^-1 k^T would be 2x"},
+                     "flops_counted": "executed flops of every launch: 2*128^2*sum over its n-tile set of (tile+1) per row (= rows*n*(n+128) for the full triangular product; the reference formulation K* K^-1 k^T would be 2x that)"},
         "extra": {"fp64_dfma_peak_tflops": dfma_peak, "dmma_register_tile_ceiling_tflops": tile_peak,
                   "dmma_register_tile_ceiling_note": "same 8x4 DMMA register tile at 8 warps/SM with changing operands and no memory traffic: the ceiling of an mma.sync FP64 GEMM at this occupancy",
                   "kernel_build_gbs": kb_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else None, "kernel_build_share": kb_ms / total_ms,
