@@ -1,17 +1,17 @@
 // Metropolis sampling of the density-matrix elements on the GPU (gple/mc.cpp:125-403).
 //
-// The reference walks one Markov chain per phase-space point (generate_markov_chain, mc.cpp:125-160) under par_unseq and
+// The reference walks one Markov chain per phase-space point (generate_markov_chain, mc.cpp:143-188) under par_unseq and
 // evaluates the target density -- the analytic initial Wigner function (mc.cpp:30-50), the GPR prediction
 // (main.cpp:75-101) or new_point_predict (evolve.cpp:425-443) -- once per step and chain.  Here all chains of an element
 // advance in LOCK-STEP: one step = proposal kernel -> ONE batched density evaluation of all n proposals (the batched
 // prediction path of gpr.cu / evolve.cu) -> accept kernel.  The analytic target needs no model, so its whole walk runs
 // inside a single kernel, one chain per thread.
 //
-// Randomness: the reference shares one clock-seeded std::mt19937 between its threads (mc.cpp:17, 137, 140), which is
+// Randomness: the reference shares one clock-seeded std::mt19937 between its threads (mc.cpp:17, 168, 173), which is
 // not reproducible; here chain i owns the counter-based stream Philox4x32-10(key = seed, counter = (i, step, stream,
 // block)) (Salmon et al., SC'11), so a run is a pure function of (seed, stream) however the chains are scheduled or
 // sharded over GPUs.  block 0 -> the two displacement uniforms of std::uniform_real_distribution(-d, d)
-// (mc.cpp:96-104), block 1 -> the acceptance uniform (mc.cpp:122, 147).
+// (mc.cpp:125-133), block 1 -> the acceptance uniform (mc.cpp:153, 173).
 #include "mc.cuh"
 
 #include <math_constants.h>
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) analytic_chains_kernel(const Analytic a, 
 		const double xn = x + (2.0 * u[0] - 1.0) * disp, pn = p + (2.0 * u[1] - 1.0) * disp;
 		const double2 rn = initial_distribution(a, xn, pn, row, col);
 		const double w_new = hypot(rn.x, rn.y);
-		if (w_new > w_old || w_new / w_old > u[2]) // mc.cpp:147
+		if (w_new > w_old || w_new / w_old > u[2]) // mc.cpp:173
 		{
 			x = xn;
 			p = pn;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) accept_kernel(double4* __restrict__ pts, 
 	double u[3];
 	chain_draws(seed, stream, chain0 + k, step, u);
 	const double w_old = hypot(pt.z, pt.w), w_new = hypot(re, im);
-	if (w_new > w_old || w_new / w_old > u[2]) // mc.cpp:147
+	if (w_new > w_old || w_new / w_old > u[2]) // mc.cpp:173
 	{
 		const double2 r = r_new[k];
 		pt = make_double4(r.x, r.y, re, im);
@@ -187,7 +187,7 @@ __global__ void coords_kernel(const double4* __restrict__ pts, const long long n
 	}
 }
 
-/// Autocorrelation of every chain (mc.cpp:187-201), one CTA per chain, accumulated into part[chain][len / 2]:
+/// Autocorrelation of every chain (mc.cpp:230-243), one CTA per chain, accumulated into part[chain][len / 2]:
 ///   part[j] = sum_i (r_i - avg) . (r_{i+j} - avg) / (len - j)
 __global__ void __launch_bounds__(256) autocorrelation_kernel(const double2* __restrict__ chains, const int len, double* __restrict__ part)
 {

@@ -14,7 +14,7 @@
 
 namespace gple_host
 {
-constexpr double MaxAcceptRatio = 0.5, MinAcceptRatio = 0.15; // gple/mc.cpp:18-19
+constexpr double MaxAcceptRatio = 0.5, MinAcceptRatio = 0.15; // gple/mc.cpp:19-20
 
 /// gple/mc.h:45-121
 class MCParameters final
@@ -59,7 +59,7 @@ public:
 		src.mass = mass;
 		src.dt = dt;
 	}
-	/// generate_markov_chain (gple/mc.cpp:125-160) for every point: points end at the last state of their chain, relabelled
+	/// generate_markov_chain (gple/mc.cpp:143-188) for every point: points end at the last state of their chain, relabelled
 	/// with the density there; returns the acceptance ratios; `chains` (optional) receives every state, n x (steps + 1) x 2
 	std::vector<double> chains(ElementPoints& pts, const std::size_t NumSteps, const double MaxDisplacement, const std::size_t RowIndex, const std::size_t ColIndex, std::vector<double>* chains_out = nullptr)
 	{
@@ -90,7 +90,7 @@ public:
 		s.col = int(ColIndex);
 		Context::check(gple_markov_chains(Context::get(), &s, reinterpret_cast<double*>(pts.data()), pts.size(), 0, 1.0, seed, 0, 0, nullptr, nullptr), "relabel");
 	}
-	/// gple/mc.cpp:187-203
+	/// gple/mc.cpp:230-243
 	std::vector<double> autocorrelation(const std::vector<double>& chain_states, const std::size_t NumChains, const std::size_t Length) const
 	{
 		std::vector<double> out(Length / 2);
@@ -104,7 +104,7 @@ private:
 	unsigned long long calls = 0;
 };
 
-/// gple/mc.cpp:286-335: the largest displacement of the list whose mean acceptance ratio lies inside (0.15, 0.5)
+/// gple/mc.cpp:288-337: the largest displacement of the list whose mean acceptance ratio lies inside (0.15, 0.5)
 inline void acceptance_optimize_displacement(MCParameters& MCParams, Sampler& sampler, const ElementPoints& density, const std::size_t RowIndex, const std::size_t ColIndex)
 {
 	static constexpr std::size_t MaxNOMC = PhaseDim * 500;
@@ -127,7 +127,7 @@ inline void acceptance_optimize_displacement(MCParameters& MCParams, Sampler& sa
 	}
 }
 
-/// gple/mc.cpp:162-260: chain length = first lag whose |autocorrelation| is within 1.1x of the minimum
+/// gple/mc.cpp:197-279: chain length = first lag whose |autocorrelation| is within 1.1x of the minimum
 inline void autocorrelation_optimize_steps(MCParameters& MCParams, Sampler& sampler, const ElementPoints& density, const std::size_t RowIndex, const std::size_t ColIndex)
 {
 	static constexpr std::size_t MaxNOMC = PhaseDim * 1000;
@@ -180,7 +180,7 @@ inline void autocorrelation_optimize_steps(MCParameters& MCParams, Sampler& samp
 	MCParams.set_num_MC_steps(min_autocor_step);
 }
 
-/// gple/mc.cpp:337-378
+/// gple/mc.cpp:339-378
 inline void element_monte_carlo(ElementPoints& density, MCParameters& MCParams, Sampler& sampler, const std::size_t RowIndex, const std::size_t ColIndex)
 {
 	acceptance_optimize_displacement(MCParams, sampler, density, RowIndex, ColIndex);

@@ -64,8 +64,8 @@ def is_very_small(density, mass, dt, kernels, pes_model, epsilon=1e-10):
 
 
 # ---- Metropolis sampling (mc.cpp:125-537) ---------------------------------------------------------------------
-MaxAcceptRatio, MinAcceptRatio = 0.5, 0.15  # mc.cpp:18-19
-PossibleDisplacement = (1e-4, 2e-4, 5e-4, 1e-3, 2e-3, 5e-3, 0.01, 0.02, 0.05, 0.1, 0.2, 0.5, 1.0, 2.0, 5.0, 10.0)  # mc.cpp:297
+MaxAcceptRatio, MinAcceptRatio = 0.5, 0.15  # mc.cpp:19-20
+PossibleDisplacement = (1e-4, 2e-4, 5e-4, 1e-3, 2e-3, 5e-3, 0.01, 0.02, 0.05, 0.1, 0.2, 0.5, 1.0, 2.0, 5.0, 10.0)  # mc.cpp:298
 ELEMENTS = ((0, 0), (1, 0), (1, 1))
 
 
@@ -127,7 +127,7 @@ class Sampler:
         return self.calls * 4 + element
 
     def chains(self, pts, num_steps, max_displacement, row, col, want_chain=False, stream=None):
-        """generate_markov_chain (mc.cpp:125-160) for all points: (pts (n, 4) at the last states, accept (n,), chains | None)"""
+        """generate_markov_chain (mc.cpp:143-188) for all points: (pts (n, 4) at the last states, accept (n,), chains | None)"""
         import ctypes as C
 
         L = self.L
@@ -142,7 +142,7 @@ class Sampler:
         return pts, accept, chains
 
     def autocorrelation(self, chains):
-        """mc.cpp:187-203"""
+        """mc.cpp:230-243"""
         L = self.L
         chains = L.f64(chains)
         out = np.empty(chains.shape[1] // 2)
@@ -158,7 +158,7 @@ class Sampler:
 
 
 def acceptance_optimize_displacement(MCParams, sampler, density, row, col):
-    """mc.cpp:286-335: the largest displacement of the list whose mean acceptance ratio lies in (0.15, 0.5)"""
+    """mc.cpp:288-337: the largest displacement of the list whose mean acceptance ratio lies in (0.15, 0.5)"""
     MaxNOMC = 2 * 500
     for d in reversed(PossibleDisplacement):
         _, accept, _ = sampler.chains(density, MaxNOMC, d, row, col)
@@ -169,7 +169,7 @@ def acceptance_optimize_displacement(MCParams, sampler, density, row, col):
 
 
 def autocorrelation_optimize_steps(MCParams, sampler, density, row, col):
-    """mc.cpp:162-260: chain length = first lag whose |autocorrelation| is within 1.1x of the minimum (with the
+    """mc.cpp:197-279: chain length = first lag whose |autocorrelation| is within 1.1x of the minimum (with the
     acceptance ratio of a chain of that length inside the window)"""
     MaxNOMC = 2 * 1000
     _, _, chains = sampler.chains(density, MaxNOMC, MCParams.get_max_displacement(), row, col, want_chain=True)
@@ -197,7 +197,7 @@ def autocorrelation_optimize_steps(MCParams, sampler, density, row, col):
 
 
 def element_monte_carlo(density, MCParams, sampler, row, col):
-    """mc.cpp:337-378: tune displacement and chain length, then walk every point and relabel it"""
+    """mc.cpp:339-378: tune displacement and chain length, then walk every point and relabel it"""
     acceptance_optimize_displacement(MCParams, sampler, density, row, col)
     autocorrelation_optimize_steps(MCParams, sampler, density, row, col)
     out, _, _ = sampler.chains(density, MCParams.get_num_MC_steps(), MCParams.get_max_displacement(), row, col)

@@ -195,8 +195,8 @@ extern "C"
 	int gple_observables(gple_ctx* ctx, int pes_model, const double* pts, size_t n, double mass, int pes_index, double out[9]);
 
 	/* ---- Metropolis sampling (gple/mc.cpp:125-403) ------------------------------------------------------
-	 * Replaces generate_markov_chain (mc.cpp:125-160) called once per point under par_unseq by element_monte_carlo
-	 * (:342-378), acceptance_optimize_displacement (:286-335) and autocorrelation_optimize_steps (:162-260): all n chains
+	 * Replaces generate_markov_chain (mc.cpp:143-188) called once per point under par_unseq by element_monte_carlo
+	 * (:339-378), acceptance_optimize_displacement (:288-337) and autocorrelation_optimize_steps (:197-279): all n chains
 	 * of one element advance in lock-step, one batched density evaluation per step.  Target density
 	 * distribution(r, row, col) of the reference's DistributionFunction:
 	 *   GPLE_MC_ANALYTIC   initial_distribution (mc.cpp:30-50), analytic = {x0, p0, sigma_x, sigma_p, pop0, pop1, phase0, phase1}
@@ -222,7 +222,7 @@ extern "C"
 	/* pts: n x 4 (x, p, Re rho, Im rho), start points in, last state of every chain and its density out (mc.cpp:366-369).
 	 * accept_ratio: n doubles or NULL.  chains: n x (num_steps + 1) x 2 doubles (every state of every chain) or NULL. */
 	int gple_markov_chains(gple_ctx* ctx, const gple_mc_source* source, double* pts, size_t n, size_t num_steps, double max_displacement, unsigned long long seed, unsigned long long stream, unsigned long long chain0, double* accept_ratio, double* chains);
-	/* Mean autocorrelation of the chains (mc.cpp:187-203): out[j] = mean_k sum_i (r_i - <r>).(r_{i+j} - <r>) / (len - j), j < len / 2 */
+	/* Mean autocorrelation of the chains (mc.cpp:230-243): out[j] = mean_k sum_i (r_i - <r>).(r_{i+j} - <r>) / (len - j), j < len / 2 */
 	int gple_chain_autocorrelation(gple_ctx* ctx, const double* chains, size_t n, size_t len, double* out);
 
 	/* ---- measurement helpers (bench.py) --------------------------------------------------------------- */

@@ -443,7 +443,7 @@ extern "C"
 	{
 		return nlml_complex(*static_cast<const TrainingComplexKernel*>(h), grad);
 	}
-	// ---- Metropolis sampling (gple/mc.cpp:125-203) -------------------------------------------------------
+	// ---- Metropolis sampling (gple/mc.cpp:143-243) -------------------------------------------------------
 	/// kind 0: analytic initial distribution (analytic[8] as in orc_evolve); 1: predict_distribution of the models
 	/// (main.cpp:75-101); 2: new_point_predict over the models (evolve.cpp:425-443, needs model / mass / dt).
 	/// pts: n x 4 (x, p, re, im) in/out; accept: n doubles or NULL; chain_out: n x (num_steps + 1) x 2 or NULL.

@@ -3,7 +3,7 @@
 // autocorrelation_optimize_steps (:176-203).
 //
 // The reference draws from one clock-seeded std::mt19937 shared un-synchronised between the threads of par_unseq
-// (mc.cpp:17, 137, 140), so its chains are not reproducible even against itself.  To make the sampler testable, chain
+// (mc.cpp:17, 168, 173), so its chains are not reproducible even against itself.  To make the sampler testable, chain
 // i draws from its own counter-based stream: Philox4x32-10 (Salmon et al., SC'11; the published constants below), key =
 // the 64-bit seed, counter = (chain index low, chain index high, step, stream << 1 | block), block 0 -> the two
 // displacement uniforms, block 1 -> the acceptance uniform.  A uniform double takes 53 bits of two output words.
@@ -51,7 +51,7 @@ struct Philox
 	}
 };
 
-/// generate_markov_chain (gple/mc.cpp:125-160) for chain `chain` starting at (x, p).
+/// generate_markov_chain (gple/mc.cpp:143-188) for chain `chain` starting at (x, p).
 /// chain_out (optional): 2 * (num_steps + 1) doubles.  Returns the acceptance ratio; (x, p) and rho end at the last state.
 inline double markov_chain(const Distribution& distribution, const std::size_t row, const std::size_t col, double& x, double& p, cplx& rho, const std::size_t num_steps, const double max_displacement, const std::uint64_t seed, const std::uint64_t stream, const std::uint64_t chain, double* chain_out)
 {
@@ -66,11 +66,11 @@ inline double markov_chain(const Distribution& distribution, const std::size_t r
 	for (std::size_t it = 0; it < num_steps; it++)
 	{
 		const auto u = Philox::draws(seed, stream, chain, std::uint32_t(it));
-		// std::uniform_real_distribution(-d, d) (mc.cpp:96-104)
+		// std::uniform_real_distribution(-d, d) (mc.cpp:125-133)
 		const double xn = x + (2.0 * u[0] - 1.0) * max_displacement, pn = p + (2.0 * u[1] - 1.0) * max_displacement;
 		const cplx rho_new = distribution(xn, pn, row, col);
 		const double weight_new = std::abs(rho_new);
-		if (weight_new > weight_old || weight_new / weight_old > u[2]) // mc.cpp:147
+		if (weight_new > weight_old || weight_new / weight_old > u[2]) // mc.cpp:173
 		{
 			x = xn;
 			p = pn;
@@ -87,7 +87,7 @@ inline double markov_chain(const Distribution& distribution, const std::size_t r
 	return num_steps > 0 ? double(acc) / double(num_steps) : 0.0;
 }
 
-/// Autocorrelation of one chain (gple/mc.cpp:187-201): out[j] = sum_i (r_i - avg).(r_{i+j} - avg) / (len - j), j < len / 2
+/// Autocorrelation of one chain (gple/mc.cpp:230-243): out[j] = sum_i (r_i - avg).(r_{i+j} - avg) / (len - j), j < len / 2
 inline void chain_autocorrelation(const double* chain, const std::size_t len, double* out)
 {
 	double ax = 0.0, ap = 0.0;

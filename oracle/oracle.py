@@ -279,7 +279,7 @@ def initial_distribution(analytic, r, row, col):
 
 
 def markov_chains(pts, num_steps, max_displacement, seed, stream, row, col, analytic=None, k00=None, k10=None, k11=None, new_point=None, want_chain=False):
-    """gple/mc.cpp:125-160 for every point of pts (n, 4) at once, chain i on Philox stream (seed, stream, i).
+    """gple/mc.cpp:143-188 for every point of pts (n, 4) at once, chain i on Philox stream (seed, stream, i).
     Distribution: analytic[8] (initial_distribution), else predict_distribution of the models, else -- with
     new_point = (model, mass, dt) -- new_point_predict.  Returns (pts_out (n, 4), accept (n,), chains (n, steps + 1, 2) | None)."""
     pts = np.array(_f64(pts), copy=True)
@@ -294,7 +294,7 @@ def markov_chains(pts, num_steps, max_displacement, seed, stream, row, col, anal
 
 
 def chain_autocorrelation(chains):
-    """gple/mc.cpp:187-203: mean autocorrelation over the chains, chains (n, len, 2) -> (len // 2,)"""
+    """gple/mc.cpp:230-243: mean autocorrelation over the chains, chains (n, len, 2) -> (len // 2,)"""
     chains = _f64(chains)
     n, length = chains.shape[0], chains.shape[1]
     out = np.empty(length // 2)

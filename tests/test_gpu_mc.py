@@ -1,5 +1,5 @@
 """Metropolis sampling on the GPU (gple_markov_chains, gple_chain_autocorrelation) against the oracle's per-chain walk
-(gple/mc.cpp:125-203) on the same Philox streams: every accept / reject decision, every chain state and the relabelled
+(gple/mc.cpp:143-243) on the same Philox streams: every accept / reject decision, every chain state and the relabelled
 densities must agree; the tuning logic of mc.py must then make the same choices on either backend."""
 import numpy as np
 import pytest
