@@ -54,7 +54,7 @@ inline ParameterVector local_parameter_to_global(ParameterVector p)
 	}
 	return p;
 }
-/// gple/opt.cpp:151-187
+/// gple/opt.cpp:197-232
 inline ParameterVector global_parameter_to_local(ParameterVector p)
 {
 	for (const std::size_t i : log_positions(p.size()))
@@ -63,7 +63,7 @@ inline ParameterVector global_parameter_to_local(ParameterVector p)
 	}
 	return p;
 }
-/// gple/opt.cpp:193-232: d/d(ln x) = x d/dx
+/// gple/opt.cpp:155-191: d/d(ln x) = x d/dx
 inline ParameterVector local_gradient_to_global(const ParameterVector& local, ParameterVector grad)
 {
 	for (const std::size_t i : log_positions(local.size()))
@@ -73,9 +73,9 @@ inline ParameterVector local_gradient_to_global(const ParameterVector& local, Pa
 	return grad;
 }
 
-using ElementTrainingParameters = std::tuple<const ElementTrainingSet&, const ElementTrainingSet&>;					   // opt.cpp:434
-using AnalyticalLooseFunctionParameters = std::tuple<const AllTrainingSets&, const AllTrainingSets&>;					   // opt.cpp:589
-using AnalyticalConstraintParameters = std::tuple<const AllTrainingSets&, const QuantumVectorD&, const double&, const double&>; // opt.cpp:638
+using ElementTrainingParameters = std::tuple<const ElementTrainingSet&, const ElementTrainingSet&>;					   // opt.cpp:16
+using AnalyticalLooseFunctionParameters = std::tuple<const AllTrainingSets&, const AllTrainingSets&>;					   // opt.cpp:19
+using AnalyticalConstraintParameters = std::tuple<const AllTrainingSets&, const QuantumVectorD&, const double&, const double&>; // opt.cpp:22
 
 /// loose_function (gple/opt.cpp:441-482): LOOCV error of the training set + squared error on the extra set.  Written like the
 /// reference's body -- a TrainingKernel on the training set, then the prediction error on the extra set -- with the trained model

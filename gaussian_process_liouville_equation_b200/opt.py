@@ -56,7 +56,7 @@ def local_parameter_to_global(param):
 
 
 def global_parameter_to_local(param):
-    """opt.cpp:151-187"""
+    """opt.cpp:197-232"""
     r = np.array(param, dtype=np.float64)
     idx = _log_indices(len(r))
     r[idx] = np.exp(r[idx])
@@ -64,7 +64,7 @@ def global_parameter_to_local(param):
 
 
 def local_gradient_to_global(param_local, grad_local):
-    """opt.cpp:194-232: d/d(ln p) = p d/dp"""
+    """opt.cpp:155-191: d/d(ln p) = p d/dp"""
     r = np.array(grad_local, dtype=np.float64)
     idx = _log_indices(len(r))
     r[idx] = r[idx] * np.asarray(param_local)[idx]
