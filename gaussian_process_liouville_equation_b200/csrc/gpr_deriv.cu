@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(1024) nlml_scalars_kernel(const double* __rest
 }
 
 /// tr[(M - w w^T) D] = sum_IJ (M_IJ - w_I w_J) D(I, J) for a composite matrix D generated on the fly (never stored):
-/// the gradient of the NLML (test/gpr.cpp:487-493, :523).  One CTA per 128 x 128 tile; partials summed by sum_kernel-like pass.
+/// the gradient of the NLML (test/gpr.cpp:487-493, :525).  One CTA per 128 x 128 tile; partials summed by sum_kernel-like pass.
 __global__ void __launch_bounds__(256) trace_quad_kernel(const CompTerms ct, const double2* __restrict__ X, const int N, const int Np, const int n, const double* __restrict__ M, const double* __restrict__ w, double* __restrict__ part)
 {
 	__shared__ double2 xr[128], xc[128];

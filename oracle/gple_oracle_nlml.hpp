@@ -2,7 +2,7 @@
 // reference's test programme minimises (test/gpr.cpp:470-532; formula doc :475-496), restated for the gple/ element
 // models so that it can serve as an alternative loss on the same kernels:
 //     NLML = y'^T K^-1 y' / 2 + sum_i ln L_ii        (the constant n/2 ln 2 pi is dropped, test/gpr.cpp:481-483)
-//     d NLML / d theta = tr[(K^-1 - b b^T) dK/dtheta] / 2,   b = K^-1 y'      (test/gpr.cpp:487-493, :523)
+//     d NLML / d theta = tr[(K^-1 - b b^T) dK/dtheta] / 2,   b = K^-1 y'      (test/gpr.cpp:487-493, :525)
 // y' are the model's rescaled labels (kernel.cpp:279-280 / complex_kernel.cpp:262-263).  The reference has no NLML
 // for the complex element; there the likelihood is that of the real composite process [Re f; Im f] whose covariance
 // is [[K_rr, K_ri], [K_ri, K_ii]] with K = K_rr + K_ii, Kt = K_rr - K_ii + 2i K_ri (complex_kernel.h:12-13).
@@ -13,7 +13,7 @@
 
 namespace orc
 {
-/// Unpivoted Cholesky (Eigen::LLT of test/gpr.cpp:512); returns false if not positive definite.
+/// Unpivoted Cholesky (Eigen::LLT of test/gpr.cpp:511); returns false if not positive definite.
 inline bool llt_lower(Mat& A)
 {
 	const std::size_t n = A.rows;
