@@ -17,7 +17,9 @@
 #include <array>
 #include <cassert>
 #include <complex>
-#include <future>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <limits>
 #include <atomic>
 #include <memory>
@@ -115,26 +117,156 @@ struct ContextSlot
 	ContextSlot& operator=(const ContextSlot&) = delete;
 };
 
+/// Two persistent worker threads, bound to the context slots 1 and 2 (slot 0 is the calling thread).  An optimisation makes
+/// thousands of three-element evaluations of a millisecond or less each: spawning threads per evaluation would cost as much as
+/// the evaluation itself.
+class ElementWorkers
+{
+public:
+	static ElementWorkers& instance()
+	{
+		static ElementWorkers w;
+		return w;
+	}
+	static bool& inside_worker()
+	{
+		static thread_local bool flag = false;
+		return flag;
+	}
+	void post(const int k, std::function<void()> job)
+	{
+		Worker& w = Workers[k - 1];
+		{
+			const std::lock_guard<std::mutex> lock(w.m);
+			w.job = std::move(job);
+			w.busy = true;
+			w.error = nullptr;
+		}
+		w.cv.notify_all();
+	}
+	/// wait for worker k; re-throws what its job threw
+	void wait(const int k)
+	{
+		Worker& w = Workers[k - 1];
+		std::unique_lock<std::mutex> lock(w.m);
+		w.cv.wait(lock, [&w]() { return !w.busy; });
+		if (w.error)
+		{
+			std::rethrow_exception(w.error);
+		}
+	}
+
+private:
+	struct Worker
+	{
+		std::mutex m;
+		std::condition_variable cv;
+		std::function<void()> job;
+		bool busy = false, stop = false;
+		std::exception_ptr error;
+		std::thread th;
+	};
+	std::array<Worker, 2> Workers;
+	ElementWorkers()
+	{
+		for (int k = 1; k <= 2; k++)
+		{
+			Worker& w = Workers[k - 1];
+			w.th = std::thread(
+				[&w, k]()
+				{
+					const ContextSlot guard(k);
+					inside_worker() = true;
+					std::unique_lock<std::mutex> lock(w.m);
+					while (true)
+					{
+						w.cv.wait(lock, [&w]() { return w.busy || w.stop; });
+						if (w.stop)
+						{
+							return;
+						}
+						std::function<void()> job = std::move(w.job);
+						lock.unlock();
+						std::exception_ptr err;
+						try
+						{
+							job();
+						}
+						catch (...)
+						{
+							err = std::current_exception();
+						}
+						lock.lock();
+						w.error = err;
+						w.busy = false;
+						w.cv.notify_all();
+					}
+				}
+			);
+		}
+	}
+	~ElementWorkers()
+	{
+		for (Worker& w : Workers)
+		{
+			{
+				const std::lock_guard<std::mutex> lock(w.m);
+				w.stop = true;
+			}
+			w.cv.notify_all();
+			if (w.th.joinable())
+			{
+				w.th.join();
+			}
+		}
+	}
+};
+
 /// Run f(0), f(1), f(2) concurrently, f(k) on the context of slot k; exceptions are re-thrown in the caller.
 template <typename F>
 inline void for_each_element_concurrently(F&& f)
 {
-	std::array<std::future<void>, 2> others;
-	for (int k = 1; k < 3; k++)
+	if (ElementWorkers::inside_worker())
 	{
-		others[k - 1] = std::async(
-			std::launch::async,
-			[&f, k]()
-			{
-				const ContextSlot guard(k);
-				f(std::size_t(k));
-			}
-		);
+		// already on a worker (no caller in this library nests, but a nested call must not wait for its own thread)
+		for (std::size_t k = 0; k < 3; k++)
+		{
+			f(k);
+		}
+		return;
 	}
-	f(std::size_t(0));
-	for (auto& o : others)
+	Context::get(); // the contexts exist before the workers use them
+	ElementWorkers& workers = ElementWorkers::instance();
+	workers.post(1, [&f]() { f(std::size_t(1)); });
+	workers.post(2, [&f]() { f(std::size_t(2)); });
+	std::exception_ptr mine;
+	try
 	{
-		o.get();
+		f(std::size_t(0));
+	}
+	catch (...)
+	{
+		mine = std::current_exception();
+	}
+	std::exception_ptr theirs;
+	for (int k = 1; k <= 2; k++)
+	{
+		try
+		{
+			workers.wait(k);
+		}
+		catch (...)
+		{
+			theirs = std::current_exception();
+		}
+	}
+	if (mine)
+	{
+		std::rethrow_exception(mine);
+	}
+	if (theirs)
+	{
+		std::rethrow_exception(theirs);
 	}
 }
 

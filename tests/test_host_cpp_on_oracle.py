@@ -129,7 +129,7 @@ def test_cpp_optimiser_three_elements_logic(tmp_path):
     from test_opt_cpp import write_points
 
     exe = compile_on_mock(os.path.join(ROOT, "tests", "cpp", "opt_test.cpp"), "opt_test")
-    n, centre = 24, (0.0, syn.P0)
+    n, centre = 16, (0.0, syn.P0)
     density, extra = [], []
     for e in range(3):
         X, y = syn.training_set(63, e, n, centre)
@@ -140,7 +140,7 @@ def test_cpp_optimiser_three_elements_logic(tmp_path):
     e0 = 0.6 * o[0][7] / o[0][0] + 0.4 * o[1][7] / o[1][0]
     path = os.path.join(tmp_path, "points.txt")
     write_points(path, density, extra)
-    got = parse(subprocess.run([exe, path, "1", repr(syn.MASS), repr(e0), repr(syn.snapshot_purity()), "60", "150"], capture_output=True, text=True, check=True, timeout=900).stdout)
+    got = parse(subprocess.run([exe, path, "1", repr(syn.MASS), repr(e0), repr(syn.snapshot_purity()), "40", "80"], capture_output=True, text=True, check=True, timeout=900).stdout)
     assert np.isfinite(got["error"]) and got["error"] >= 0.0
     assert abs(got["population"] - 1.0) < 0.2 and abs(got["energy"] / e0 - 1.0) < 0.2
     for e, npar in enumerate((4, 8, 4)):
@@ -152,9 +152,9 @@ def test_main_loop_logic_at_the_crossing():
     """Started at the crossing the run must populate rho10 and rho11: is_very_small, new_element_point_selection (Metropolis
     tuning on the new_point_predict target, extra points) and the element-change re-optimisation of main.cpp:145-162."""
     exe = compile_on_mock(os.path.join(ROOT, "examples", "mqcle_run.cpp"), "mqcle_run")
-    out = subprocess.run([exe, "16", "2", "0", "1", "7", "-0.3"], capture_output=True, text=True, check=True, timeout=900).stdout
+    out = subprocess.run([exe, "12", "2", "0", "1", "7", "-0.3"], capture_output=True, text=True, check=True, timeout=900).stdout
     ticks = [[float(v) for v in line.split()[2:]] for line in out.splitlines() if line.startswith("tick ")]
     info = {line.split()[0]: line.split()[1:] for line in out.splitlines() if not line.startswith("tick ")}
-    assert len(ticks) == 3 and info["elements"] == ["16", "16", "16"] and int(info["optimisations"][0]) >= 2
+    assert len(ticks) == 3 and info["elements"] == ["12", "12", "12"] and int(info["optimisations"][0]) >= 2
     for pop, e, pur in ticks:
         assert 0.8 < pop < 1.2 and 0.8 < pur < 1.2
