@@ -126,8 +126,10 @@ class Sampler:
         self.calls += 1
         return self.calls * 4 + element
 
-    def chains(self, pts, num_steps, max_displacement, row, col, want_chain=False, stream=None):
-        """generate_markov_chain (mc.cpp:143-188) for all points: (pts (n, 4) at the last states, accept (n,), chains | None)"""
+    def chains(self, pts, num_steps, max_displacement, row, col, want_chain=False, stream=None, chain0=0):
+        """generate_markov_chain (mc.cpp:143-188) for all points: (pts (n, 4) at the last states, accept (n,), chains | None).
+        Point k walks the Philox stream of chain `chain0 + k`: a rank that owns the block [lo, hi) of a sharded point set passes
+        chain0 = lo and gets exactly the states it would have had in the whole set."""
         import ctypes as C
 
         L = self.L
@@ -137,7 +139,7 @@ class Sampler:
         accept = np.empty(n)
         chains = np.empty((n, num_steps + 1, 2)) if want_chain else None
         src = self._source(row, col)
-        self.ctx.check(self.ctx.lib.gple_markov_chains(self.ctx.h, C.byref(src), L.addr(pts), n, int(num_steps), float(max_displacement), self.seed, int(stream), 0, L.addr(accept),
+        self.ctx.check(self.ctx.lib.gple_markov_chains(self.ctx.h, C.byref(src), L.addr(pts), n, int(num_steps), float(max_displacement), self.seed, int(stream), int(chain0), L.addr(accept),
                                                        L.addr(chains) if want_chain else None))
         return pts, accept, chains
 

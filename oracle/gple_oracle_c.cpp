@@ -447,7 +447,8 @@ extern "C"
 	/// kind 0: analytic initial distribution (analytic[8] as in orc_evolve); 1: predict_distribution of the models
 	/// (main.cpp:75-101); 2: new_point_predict over the models (evolve.cpp:425-443, needs model / mass / dt).
 	/// pts: n x 4 (x, p, re, im) in/out; accept: n doubles or NULL; chain_out: n x (num_steps + 1) x 2 or NULL.
-	void orc_markov_chains(int kind, const double* analytic, const void* h00, const void* h10, const void* h11, int model, double mass, double dt, int row, int col, double* pts, std::size_t n, std::size_t num_steps, double max_displacement, std::uint64_t seed, std::uint64_t stream, double* accept, double* chain_out)
+	/// Point k walks chain chain0 + k (a block of a sharded point set keeps the streams it would have in the whole set).
+	void orc_markov_chains(int kind, const double* analytic, const void* h00, const void* h10, const void* h11, int model, double mass, double dt, int row, int col, double* pts, std::size_t n, std::size_t num_steps, double max_displacement, std::uint64_t seed, std::uint64_t stream, std::uint64_t chain0, double* accept, double* chain_out)
 	{
 		Predictors pr;
 		pr.diag[0] = static_cast<const TrainingKernel*>(h00);
@@ -476,7 +477,7 @@ extern "C"
 			{
 				double x = pts[4 * k], p = pts[4 * k + 1];
 				cplx rho;
-				const double a = markov_chain(dist, std::size_t(row), std::size_t(col), x, p, rho, num_steps, max_displacement, seed, stream, k, chain_out != nullptr ? chain_out + k * 2 * (num_steps + 1) : nullptr);
+				const double a = markov_chain(dist, std::size_t(row), std::size_t(col), x, p, rho, num_steps, max_displacement, seed, stream, chain0 + k, chain_out != nullptr ? chain_out + k * 2 * (num_steps + 1) : nullptr);
 				pts[4 * k] = x;
 				pts[4 * k + 1] = p;
 				pts[4 * k + 2] = rho.real();

@@ -278,7 +278,7 @@ def initial_distribution(analytic, r, row, col):
     return out
 
 
-def markov_chains(pts, num_steps, max_displacement, seed, stream, row, col, analytic=None, k00=None, k10=None, k11=None, new_point=None, want_chain=False):
+def markov_chains(pts, num_steps, max_displacement, seed, stream, row, col, analytic=None, k00=None, k10=None, k11=None, new_point=None, want_chain=False, chain0=0):
     """gple/mc.cpp:143-188 for every point of pts (n, 4) at once, chain i on Philox stream (seed, stream, i).
     Distribution: analytic[8] (initial_distribution), else predict_distribution of the models, else -- with
     new_point = (model, mass, dt) -- new_point_predict.  Returns (pts_out (n, 4), accept (n,), chains (n, steps + 1, 2) | None)."""
@@ -289,7 +289,7 @@ def markov_chains(pts, num_steps, max_displacement, seed, stream, row, col, anal
     accept = np.empty(n)
     chains = np.empty((n, num_steps + 1, 2)) if want_chain else None
     lib().orc_markov_chains(kind, _p(None if analytic is None else _f64(analytic)), _h(k00), _h(k10), _h(k11), int(model), C.c_double(mass), C.c_double(dt), int(row), int(col), _p(pts),
-                            C.c_size_t(n), C.c_size_t(num_steps), C.c_double(max_displacement), C.c_uint64(seed), C.c_uint64(stream), _p(accept), _p(chains))
+                            C.c_size_t(n), C.c_size_t(num_steps), C.c_double(max_displacement), C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(chain0), _p(accept), _p(chains))
     return pts, accept, chains
 
 

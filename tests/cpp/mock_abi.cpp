@@ -191,11 +191,8 @@ extern "C"
 	}
 	int gple_markov_chains(gple_ctx* ctx, const gple_mc_source* s, double* pts, size_t n, size_t num_steps, double max_displacement, unsigned long long seed, unsigned long long stream, unsigned long long chain0, double* accept_ratio, double* chains)
 	{
-		if (chain0 != 0)
-		{
-			return fail(ctx, "gple_markov_chains: the mock walks chains from index 0 only");
-		}
-		orc_markov_chains(s->kind, s->analytic, handle(s->m00), handle(s->m10), handle(s->m11), s->pes_model, s->mass, s->dt, s->row, s->col, pts, n, num_steps, max_displacement, seed, stream, accept_ratio, chains);
+		(void)ctx;
+		orc_markov_chains(s->kind, s->analytic, handle(s->m00), handle(s->m10), handle(s->m11), s->pes_model, s->mass, s->dt, s->row, s->col, pts, n, num_steps, max_displacement, seed, stream, chain0, accept_ratio, chains);
 		return GPLE_OK;
 	}
 	int gple_chain_autocorrelation(gple_ctx*, const double* chains, size_t n, size_t len, double* out)

@@ -74,14 +74,14 @@ class Sampler:
         self.calls += 1
         return self.calls * 4 + element
 
-    def chains(self, pts, num_steps, max_displacement, row, col, want_chain=False, stream=None):
+    def chains(self, pts, num_steps, max_displacement, row, col, want_chain=False, stream=None, chain0=0):
         stream = self.next_stream(row + col) if stream is None else stream
         analytic = None
         if self.analytic is not None:
             r0, s0, pop, ph = self.analytic
             analytic = [r0[0], r0[1], s0[0], s0[1], pop[0], pop[1], ph[0], ph[1]]
         k = [None, None, None] if self.kernels is None else [getattr(x, "o", x) for x in self.kernels]
-        return orc.markov_chains(pts, num_steps, max_displacement, self.seed, stream, row, col, analytic=analytic, k00=k[0], k10=k[1], k11=k[2], new_point=self.new_point, want_chain=want_chain)
+        return orc.markov_chains(pts, num_steps, max_displacement, self.seed, stream, row, col, analytic=analytic, k00=k[0], k10=k[1], k11=k[2], new_point=self.new_point, want_chain=want_chain, chain0=chain0)
 
     def autocorrelation(self, chains):
         return orc.chain_autocorrelation(chains)

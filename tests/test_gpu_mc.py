@@ -109,3 +109,19 @@ def test_cpp_host_monte_carlo_selection_matches_oracle_sampler(tmp_path):
         assert got[f"displacement{e}"] == params[e].get_max_displacement() and got[f"steps{e}"] == params[e].get_num_MC_steps()
         walked = np.array([[got[f"p{e}_{i}_{c}"] for c in ("x", "p", "re", "im")] for i in range(len(pts))])
         assert np.abs(walked - ref[e]).max() <= 1e-12 * np.abs(ref[e]).max()
+
+
+def test_chain_blocks_reproduce_the_whole_set():
+    """chain0: a block [lo, hi) of the points walked with chain0 = lo ends exactly where it ends inside the whole set
+    (what a rank of a multi-GPU run does with its shard)."""
+    pts = start_points(90, 101, (syn.X0, syn.P0))
+    whole, acc, _ = mc.Sampler(13, analytic=ANALYTIC).chains(pts, 60, 0.5, 1, 0, stream=3)
+    parts = [mc.Sampler(13, analytic=ANALYTIC).chains(pts[lo:hi], 60, 0.5, 1, 0, stream=3, chain0=lo) for lo, hi in ((0, 40), (40, 101))]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), whole) and np.array_equal(np.concatenate([p[1] for p in parts]), acc)
+    centre = (0.0, syn.P0)
+    g, _ = models(96, centre)
+    pts = start_points(91, 50, centre)
+    whole, acc, _ = mc.Sampler(13, kernels=g).chains(pts, 15, 0.3, 0, 0, stream=4)
+    parts = [mc.Sampler(13, kernels=g).chains(pts[lo:hi], 15, 0.3, 0, 0, stream=4, chain0=lo) for lo, hi in ((0, 17), (17, 50))]
+    got = np.concatenate([p[0] for p in parts])
+    assert np.array_equal(got[:, :2], whole[:, :2]) and np.abs(got[:, 2:] - whole[:, 2:]).max() <= 1e-12 * np.abs(whole[:, 2:]).max()

@@ -40,6 +40,34 @@ def _worker(rank, world, port, total, ret):
     dist.destroy_process_group()
 
 
+def _mc_worker(rank, world, port, total, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ORACLE_THREADS="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+
+    g = syn.rng(51, 0)
+    pts = np.zeros((total, 4))
+    pts[:, 0] = syn.X0 + syn.SIGMA_X * g.standard_normal(total)
+    pts[:, 1] = syn.P0 + syn.SIGMA_P * g.standard_normal(total)
+    an = [syn.X0, syn.P0, syn.SIGMA_X, syn.SIGMA_P, 0.8, 0.6, 0.0, 0.4]
+    lo, hi = sharding.partition(total, rank, world)
+    # every rank walks its block of the chains on the streams those chains own in the whole set (chain0 = lo)
+    mine, _, _ = orc.markov_chains(pts[lo:hi], 40, 0.5, 23, 2, 1, 0, analytic=an, chain0=lo)
+    full = sharding.all_gather_points(torch.from_numpy(mine), total).numpy()
+    if rank == 0:
+        whole, _, _ = orc.markov_chains(pts, 40, 0.5, 23, 2, 1, 0, analytic=an)
+        ret["equal"] = bool(np.array_equal(full, whole))
+    dist.destroy_process_group()
+
+
+def test_sharded_markov_chains_plus_allgather_equal_single_process():
+    """Metropolis chains are keyed by (seed, stream, chain index): a block of chains gives the same result on any rank."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_mc_worker, args=(2, _free_port(), 37, ret), nprocs=2, join=True)
+    assert ret["equal"]
+
+
 @pytest.mark.parametrize("total", [64, 37])
 def test_sharded_evolve_plus_allgather_equals_single_process(total):
     mgr = mp.Manager()
