@@ -171,3 +171,27 @@ def test_mpmath_twin_bounds_oracle_error(oracle):
     assert np.abs(k.inverse - inv_np).max() <= 1e-10 * np.abs(inv_np).max()
     assert k.error == pytest.approx(float(err), rel=1e-9)
     assert k.population == pytest.approx(float(pop), rel=1e-10)
+
+
+def test_best_effort_cpu_matches_the_oracle(oracle):
+    """oracle/best_effort.py (the BLAS / LAPACK CPU baseline that bench.py reports next to the reference-shaped port) computes
+    the same quantities as the oracle, for the real and the complex element."""
+    from oracle import best_effort as be
+
+    orc = oracle
+    X, y = syn.training_set(5, 0, 200)
+    th = np.array([1.0, 0.9 * syn.SIGMA_X, 1.1 * syn.SIGMA_P, 2e-2])
+    o, m = orc.TrainingKernel(th, X, y), be.RealModel(th, X, y)
+    Xq, _ = syn.extra_points(5, 0, X, 300)
+    p = o.predict(Xq)
+    f, var = m.predict(Xq)
+    assert m.error == pytest.approx(o.error, rel=1e-9) and m.population == pytest.approx(o.population, rel=1e-11)
+    assert np.abs(f - p["pred"]).max() <= 1e-11 * np.abs(p["pred"]).max() and np.abs(var - p["var"]).max() <= 1e-9
+    thc = np.array([1.3, 1.2, 0.8 * syn.SIGMA_X, 1.1 * syn.SIGMA_P, 0.7, 1.1 * syn.SIGMA_X, 0.9 * syn.SIGMA_P, 2e-2])
+    X, y = syn.training_set(4, 1, 150)
+    o, m = orc.TrainingComplexKernel(thc, X, y), be.ComplexModel(thc, X, y)
+    Xq, _ = syn.extra_points(4, 1, X, 200)
+    p = o.predict(Xq)
+    f, var = m.predict(Xq)
+    assert m.error == pytest.approx(o.error, rel=1e-8)
+    assert np.abs(f - p["pred"]).max() <= 1e-9 * np.abs(p["pred"]).max() and np.abs(var - p["var"]).max() <= 1e-9 * m.prior
