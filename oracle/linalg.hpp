@@ -44,13 +44,21 @@ inline unsigned num_threads()
 	return n;
 }
 
+/// 0 on a thread that may open a parallel loop, 1 inside a worker (nested loops then run serially)
+inline int& parallel_depth()
+{
+	static thread_local int depth = 0;
+	return depth;
+}
+
 /// Stand-in for the reference's `std::for_each(std::execution::par_unseq, indices...)` loops.
 template <typename F>
 inline void parallel_for(const std::size_t n, F&& f, const std::size_t min_grain = 1)
 {
 	const unsigned nt = static_cast<unsigned>(std::min<std::size_t>(num_threads(), std::max<std::size_t>(1, n / std::max<std::size_t>(1, min_grain))));
-	if (nt <= 1 || n == 0)
+	if (nt <= 1 || n == 0 || parallel_depth() > 0)
 	{
+		// serial, also for a loop nested inside a worker of an enclosing parallel loop
 		for (std::size_t i = 0; i < n; i++)
 		{
 			f(i);
@@ -64,6 +72,7 @@ inline void parallel_for(const std::size_t n, F&& f, const std::size_t min_grain
 		pool.emplace_back(
 			[t, nt, n, &f]()
 			{
+				parallel_depth() = 1;
 				const std::size_t lo = n * t / nt, hi = n * (t + 1) / nt;
 				for (std::size_t i = lo; i < hi; i++)
 				{

@@ -2,9 +2,9 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this module.  The oracle is a CPU restatement of the reference
-(kaigu1997/gaussian_process_liouville_equation, gaussian_process_liouville_equation/*.cpp); it is
-PARITY UNPINNED by the reference (no golden vectors exist) and pinned instead by
-tests/test_oracle_*.py.
+(kaigu1997/gaussian_process_liouville_equation, gaussian_process_liouville_equation/*.cpp).  The reference
+holds no golden vectors; the oracle is pinned by the reference's own translation units compiled unmodified
+into oracle/_ref (oracle/ref.py, tests/test_ref_pins_oracle.py) and by tests/test_oracle_*.py.
 """
 from __future__ import annotations
 
