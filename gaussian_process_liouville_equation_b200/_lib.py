@@ -15,7 +15,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgple_b200.so")
 
-OK, ERR_ARG, ERR_NOT_SPD, ERR_CUDA, ERR_STATE = 0, 1, 2, 3, 4
+OK, ERR_ARG, ERR_NOT_SPD, ERR_CUDA, ERR_STATE, ERR_COMM = 0, 1, 2, 3, 4, 5
+COMM_ID_BYTES = 128
 CALC_ERROR, CALC_AVERAGE, CALC_DERIVATIVE = 1, 2, 4
 SAC, DAC, ECR = 0, 1, 2
 FIELD_INVERSE, FIELD_INV_LABEL, FIELD_LABEL, FIELD_UPPER_LEFT, FIELD_LOWER_LEFT, FIELD_INV_LABEL_DERIV = 1, 2, 3, 4, 5, 8
@@ -71,6 +72,13 @@ SIGNATURES = {
     "gple_loose_function": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp, _dp, _sz, _dp, _dp, _sz, _dp]),
     "gple_pes": (C.c_int, [_vp, C.c_int, _dp, _sz, _dp, _dp, _dp]),
     "gple_evolve": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, _dp, _sz, _dp, _sz, C.c_double, C.c_double]),
+    "gple_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "gple_ctx_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p]),
+    "gple_ctx_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gple_partition": (C.c_int, [_sz, C.c_int, C.c_int, C.POINTER(_sz), C.POINTER(_sz)]),
+    "gple_allgather_points": (C.c_int, [_vp, _dp, _sz]),
+    "gple_allreduce_sum": (C.c_int, [_vp, _dp, _sz]),
+    "gple_evolve_sharded": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, _dp, _sz, _dp, _sz, C.c_double, C.c_double]),
     "gple_new_point_predict": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),
     "gple_observables": (C.c_int, [_vp, C.c_int, _dp, _sz, C.c_double, C.c_int, _dp]),
     "gple_tune_variance_gemm": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
@@ -159,6 +167,24 @@ class Context:
     def sync(self):
         self.check(self.lib.gple_ctx_sync(self.h))
 
+    # ---- multi-GPU (one process per GPU): NCCL communicator of this context ------------------------------
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        """unique_id: the 128 bytes rank 0 got from comm_unique_id(), handed over by the host's own channel."""
+        assert len(unique_id) == COMM_ID_BYTES
+        self.check(self.lib.gple_ctx_comm_init(self.h, int(rank), int(nranks), unique_id))
+
+    def comm_info(self):
+        r, n = C.c_int(), C.c_int()
+        self.check(self.lib.gple_ctx_comm_info(self.h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    def allgather_points(self, pts, total: int):
+        """in place: pts = full (total, 4) array (numpy or device tensor) with this rank's block valid"""
+        self.check(self.lib.gple_allgather_points(self.h, addr(pts), int(total)))
+
+    def allreduce_sum(self, values):
+        self.check(self.lib.gple_allreduce_sum(self.h, addr(values), int(values.size if isinstance(values, np.ndarray) else values.numel())))
+
     @property
     def launches(self) -> int:
         return int(self.lib.gple_launch_count(self.h))
@@ -197,6 +223,22 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = load().gple_comm_unique_id(buf)
+    if rc != OK:
+        raise GpleError(rc, "gple_comm_unique_id failed (NCCL not loadable?)")
+    return buf.raw
+
+
+def partition(total: int, rank: int, nranks: int):
+    lo, hi = _sz(), _sz()
+    rc = load().gple_partition(int(total), int(rank), int(nranks), C.byref(lo), C.byref(hi))
+    if rc != OK:
+        raise GpleError(rc, "gple_partition: bad rank / size")
+    return int(lo.value), int(hi.value)
 
 
 _default = None

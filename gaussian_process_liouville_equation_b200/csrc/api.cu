@@ -1,5 +1,6 @@
 // extern "C" boundary of libgple_b200.so (declared in include/gple_b200.h).
 #include "chol.cuh"
+#include "comm.cuh"
 #include "evolve.cuh"
 #include "gpr.cuh"
 #include "mc.cuh"
@@ -34,6 +35,11 @@ int guarded(gple_ctx* ctx, F&& f)
 	{
 		ctx->last_error = e.what;
 		return GPLE_ERR_ARG;
+	}
+	catch (const CommError& e)
+	{
+		ctx->last_error = e.what;
+		return GPLE_ERR_COMM;
 	}
 	catch (const std::exception& e)
 	{
@@ -270,6 +276,7 @@ extern "C"
 		}
 		cudaSetDevice(ctx->device);
 		cudaStreamSynchronize(ctx->stream);
+		comm_destroy(ctx);
 		ctx->ws.release();
 		ctx->pool.release();
 		if (ctx->h_pinned != nullptr)
@@ -716,6 +723,117 @@ extern "C"
 				double* d_pts[3] = {a.dev, b.dev, c.dev};
 				const size_t counts[3] = {n00, n10, n11};
 				evolve_device(ctx, pes_model, models, d_pts, counts, mass, dt);
+				a.finish();
+				b.finish();
+				c.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+
+	// ---- multi-GPU ----------------------------------------------------------------------------------
+	int gple_comm_unique_id(unsigned char id[GPLE_COMM_ID_BYTES])
+	{
+		if (id == nullptr)
+		{
+			return GPLE_ERR_ARG;
+		}
+		try
+		{
+			comm_unique_id(id);
+			return GPLE_OK;
+		}
+		catch (const CommError& e)
+		{
+			std::fprintf(stderr, "gple_comm_unique_id: %s\n", e.what);
+			return GPLE_ERR_COMM;
+		}
+	}
+	int gple_ctx_comm_init(gple_ctx* ctx, int rank, int nranks, const unsigned char id[GPLE_COMM_ID_BYTES])
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(id != nullptr && nranks >= 1 && rank >= 0 && rank < nranks, "gple_ctx_comm_init: bad rank / size / id");
+				comm_init(ctx, rank, nranks, id);
+				return GPLE_OK;
+			}
+		);
+	}
+	int gple_ctx_comm_info(const gple_ctx* ctx, int* rank, int* nranks)
+	{
+		if (ctx == nullptr)
+		{
+			return GPLE_ERR_ARG;
+		}
+		if (rank != nullptr)
+		{
+			*rank = ctx->comm_rank;
+		}
+		if (nranks != nullptr)
+		{
+			*nranks = ctx->comm_size;
+		}
+		return GPLE_OK;
+	}
+	int gple_partition(size_t total, int rank, int nranks, size_t* lo, size_t* hi)
+	{
+		if (lo == nullptr || hi == nullptr || nranks < 1 || rank < 0 || rank >= nranks)
+		{
+			return GPLE_ERR_ARG;
+		}
+		partition(total, rank, nranks, *lo, *hi);
+		return GPLE_OK;
+	}
+	int gple_allgather_points(gple_ctx* ctx, double* pts, size_t total)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(pts != nullptr || total == 0, "gple_allgather_points: null point set");
+				DeviceArray<double> p(ctx, pts, 4 * total, false);
+				p.write_back = true;
+				allgather_blocks(ctx, p.dev, total, 4);
+				p.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+	int gple_allreduce_sum(gple_ctx* ctx, double* values, size_t count)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(values != nullptr && count > 0, "gple_allreduce_sum: null argument");
+				DeviceArray<double> v(ctx, values, count, false);
+				v.write_back = true;
+				allreduce_sum(ctx, v.dev, count);
+				v.finish();
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
+	int gple_evolve_sharded(gple_ctx* ctx, int pes_model, const gple_model* m00, const gple_model* m10, const gple_model* m11, double* pts00, size_t n00, double* pts10, size_t n10, double* pts11, size_t n11, double mass, double dt)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(pes_model >= GPLE_SAC && pes_model <= GPLE_ECR, "gple_evolve_sharded: unknown model");
+				require((m00 == nullptr || !m00->is_complex) && (m11 == nullptr || !m11->is_complex) && (m10 == nullptr || m10->is_complex), "gple_evolve_sharded: diagonal elements take real models, rho10 a complex model");
+				require((n00 == 0 || pts00 != nullptr) && (n10 == 0 || pts10 != nullptr) && (n11 == 0 || pts11 != nullptr), "gple_evolve_sharded: null point set");
+				DeviceArray<double> a(ctx, pts00, 4 * n00, false), b(ctx, pts10, 4 * n10, false), c(ctx, pts11, 4 * n11, false);
+				a.write_back = b.write_back = c.write_back = true;
+				const gple_model* models[3] = {m00, m10, m11};
+				double* d_pts[3] = {a.dev, b.dev, c.dev};
+				const size_t totals[3] = {n00, n10, n11};
+				evolve_sharded_device(ctx, pes_model, models, d_pts, totals, mass, dt);
 				a.finish();
 				b.finish();
 				c.finish();

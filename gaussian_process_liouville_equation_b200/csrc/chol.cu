@@ -650,30 +650,24 @@ struct Chol
 };
 } // namespace
 
+/// Opt-in shared-memory sizes are a per-DEVICE function attribute: gple_ctx_create calls this once for every context,
+/// after cudaSetDevice, so that one process may hold contexts on several GPUs.
 void chol_setup_attributes()
 {
-	static bool done = false;
-	if (done)
-	{
-		return;
-	}
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::DefaultConfig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::DefaultConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::DefaultConfig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::DefaultConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::SmallConfig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SmallConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::SmallConfig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SmallConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::StripConfig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::StripConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LEAF_SMEM)));
-	done = true;
 }
 
 void gemm_nt(gple_ctx* ctx, const gemm::GemmArgs& a)
 {
-	chol_setup_attributes();
 	run_gemm(ctx, false, a);
 }
 void gemm_nn(gple_ctx* ctx, const gemm::GemmArgs& a)
 {
-	chol_setup_attributes();
 	run_gemm(ctx, true, a);
 }
 
@@ -686,7 +680,6 @@ int set_potrf_flat(const int n)
 
 void potrf_trtri(gple_ctx* ctx, double* A, double* W, const int n, int* d_info)
 {
-	chol_setup_attributes();
 	const size_t ld = size_t(n);
 	double* dinv = ctx->ws.get<double>("chol.dinv", size_t(n / LEAF) * LEAF * LEAF);
 	double* T = ctx->ws.get<double>("chol.T", size_t(n / 2 + LEAF) * size_t(n / 2 + LEAF));

@@ -134,6 +134,9 @@ struct gple_ctx
 	std::string last_error;
 	gple::Workspace ws;
 	gple::BlockPool pool; // device buffers of the element models
+	// multi-GPU: NCCL communicator of this context (ncclComm_t; NULL = single GPU), see comm.cu
+	void* comm = nullptr;
+	int comm_rank = 0, comm_size = 1;
 	double* h_pinned = nullptr; // small pinned staging area for scalar read-backs
 	size_t h_pinned_count = 0;
 	int num_sms = 148;

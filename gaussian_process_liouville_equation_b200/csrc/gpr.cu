@@ -18,6 +18,7 @@
 #include "chol.cuh"
 #include "gpr.cuh"
 #include "gpr_kernels.cuh"
+#include "mc.cuh"
 
 namespace gple
 {
@@ -328,7 +329,7 @@ struct TileSet
 };
 
 template <typename C>
-__global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* __restrict__ A, const double* __restrict__ W, const int n, double* __restrict__ q, const int rows, const TileSet ts)
+__global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* __restrict__ A, const double* __restrict__ W, const int n, double* __restrict__ part, const int rows, const TileSet ts)
 {
 	using namespace gemm;
 	extern __shared__ __align__(16) double smem[];
@@ -342,7 +343,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 	const int V = ts.count();
 	const double* Ag = A + size_t(m0) * n;
 	// When a chunk has fewer than ~148 row blocks the n-tiles are dealt round-robin to gridDim.y CTAs per row
-	// block (interleaving balances the triangular work); each writes its partial row sums to q[blockIdx.y][rows].
+	// block (interleaving balances the triangular work).  Whatever the deal, every (n-tile, column-warp) pair writes its
+	// own partial row sums to part[(v * WARPS_N + wn)][rows]; var_reduce_kernel adds them in that fixed order, so a row's
+	// result does not depend on the size or composition of the batch it was computed in (nor on the number of GPUs).
 	const int nt0 = blockIdx.y, nts = gridDim.y;
 
 	int l_v = nt0, l_nt = ts.tile(nt0), l_kt = 0, l_slot = 0;
@@ -367,12 +370,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 	{
 		issue();
 	}
-	double rowsum[C::MI];
-#pragma unroll
-	for (int i = 0; i < C::MI; i++)
-	{
-		rowsum[i] = 0.0;
-	}
 	double acc[C::MI][C::NJ][2];
 	int c_slot = 0;
 	for (int v = nt0; v < V; v += nts)
@@ -387,57 +384,41 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 			compute_stage<C, false>(acc, As + c_slot * C::A_STAGE, Bs + c_slot * C::B_STAGE, wm, wn, g, t);
 			c_slot = (c_slot + 1 == C::STAGES) ? 0 : c_slot + 1;
 		}
+		// this warp's share of the tile: sum of squares over its C::NJ * 8 columns, per row (quad reduction over the columns)
+		double* dst = part + (size_t(v) * C::WARPS_N + wn) * rows + m0 + wm * C::WTM + g;
 #pragma unroll
 		for (int i = 0; i < C::MI; i++)
 		{
+			double s = 0.0;
 #pragma unroll
 			for (int j = 0; j < C::NJ; j++)
 			{
-				rowsum[i] = fma(acc[i][j][0], acc[i][j][0], rowsum[i]);
-				rowsum[i] = fma(acc[i][j][1], acc[i][j][1], rowsum[i]);
+				s = fma(acc[i][j][0], acc[i][j][0], s);
+				s = fma(acc[i][j][1], acc[i][j][1], s);
+			}
+			s += __shfl_xor_sync(0xffffffffu, s, 1);
+			s += __shfl_xor_sync(0xffffffffu, s, 2);
+			if (t == 0)
+			{
+				dst[i * 8] = s;
 			}
 		}
 	}
 	cp_async_wait<0>();
-	__syncthreads();
-	// reduce over the 4 lanes of a quad (columns) and over the column-warps
-	double* red = smem; // [WARPS_N][128]
-#pragma unroll
-	for (int i = 0; i < C::MI; i++)
-	{
-		double s = rowsum[i];
-		s += __shfl_xor_sync(0xffffffffu, s, 1);
-		s += __shfl_xor_sync(0xffffffffu, s, 2);
-		if (t == 0)
-		{
-			red[wn * BM + wm * C::WTM + i * 8 + g] = s;
-		}
-	}
-	__syncthreads();
-	if (tid < BM)
-	{
-		double s = 0.0;
-#pragma unroll
-		for (int w = 0; w < C::WARPS_N; w++)
-		{
-			s += red[w * BM + tid];
-		}
-		q[size_t(blockIdx.y) * rows + m0 + tid] = s;
-	}
 }
 
-/// q[r] = sum over the n-splits of the partial row sums
-__global__ void var_reduce_kernel(double* __restrict__ q, const int rows, const int splits)
+/// q[r] = sum of the `count` partial row sums of a launch (count = n-tiles of the set x column-warps), in storage order
+__global__ void var_reduce_kernel(const double* __restrict__ part, double* __restrict__ q, const int rows, const int count)
 {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= rows)
 	{
 		return;
 	}
-	double s = q[r];
-	for (int k = 1; k < splits; k++)
+	double s = 0.0;
+	for (int k = 0; k < count; k++)
 	{
-		s += q[size_t(k) * rows + r];
+		s += part[size_t(k) * rows + r];
 	}
 	q[r] = s;
 }
@@ -457,12 +438,6 @@ int g_var_variant = 1; // BK = 32, 3 stages, 2 x 4 warps: 88.8 % of the DMMA pea
 template <typename C>
 void launch_var_gemm_cfg(gple_ctx* ctx, const double* A, const double* W, int n, int rows, double* q, const TileSet& ts)
 {
-	static bool attr_done = false;
-	if (!attr_done)
-	{
-		GPLE_CUDA(cudaFuncSetAttribute(var_gemm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM_BYTES)));
-		attr_done = true;
-	}
 	// choose the number of n-splits S that minimises the makespan ceil(blocks * S / SMs) / S
 	const int mb = rows / 128, T = ts.count();
 	int best = 1;
@@ -476,11 +451,9 @@ void launch_var_gemm_cfg(gple_ctx* ctx, const double* A, const double* W, int n,
 			best = S;
 		}
 	}
-	GPLE_LAUNCH(ctx, var_gemm_kernel<C>, dim3(mb, best), C::THREADS, C::SMEM_BYTES, A, W, n, q, rows, ts);
-	if (best > 1)
-	{
-		GPLE_LAUNCH(ctx, var_reduce_kernel, (rows + 255) / 256, 256, 0, q, rows, best);
-	}
+	double* part = ctx->ws.get<double>("pred.qpart", size_t(rows) * size_t(T) * C::WARPS_N);
+	GPLE_LAUNCH(ctx, var_gemm_kernel<C>, dim3(mb, best), C::THREADS, C::SMEM_BYTES, A, W, n, part, rows, ts);
+	GPLE_LAUNCH(ctx, var_reduce_kernel, (rows + 255) / 256, 256, 0, part, q, rows, T * C::WARPS_N);
 }
 
 /// flops executed by a launch over `rows` rows: 2 * 128^2 * sum over the tile set of (tile + 1) per row
@@ -1193,15 +1166,27 @@ void require_rows(long long total_rows)
 
 } // namespace
 
+namespace
+{
+template <typename C>
+void var_gemm_attribute()
+{
+	GPLE_CUDA(cudaFuncSetAttribute(var_gemm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM_BYTES)));
+}
+} // namespace
+
+/// Per-device function attributes of every kernel with opt-in shared memory (called by gple_ctx_create on the context's device).
 void gpr_setup_attributes()
 {
-	static bool done = false;
-	if (done)
-	{
-		return;
-	}
 	chol_setup_attributes();
-	done = true;
+	var_gemm_attribute<VarCfg0>();
+	var_gemm_attribute<VarCfg1>();
+	var_gemm_attribute<VarCfg2>();
+	var_gemm_attribute<VarCfg3>();
+	var_gemm_attribute<VarCfg4>();
+	var_gemm_attribute<VarCfg5>();
+	var_gemm_attribute<VarCfg6>();
+	mc_setup_attributes();
 }
 
 void free_model(gple_ctx* ctx, gple_model* m)
@@ -1242,7 +1227,6 @@ void ensure_full_inverse(gple_ctx* ctx, gple_model* m)
 
 int train_real(gple_ctx* ctx, const double* X_, const double* y_, size_t N, const double* theta, unsigned flags, gple_model** out_model, gple_real_scalars* out)
 {
-	gpr_setup_attributes();
 	DeviceArray<double> X(ctx, X_, 2 * N, false), y(ctx, y_, 2 * N, false);
 	gple_model* m = new gple_model();
 	m->owner = ctx;
@@ -1309,7 +1293,6 @@ int train_real(gple_ctx* ctx, const double* X_, const double* y_, size_t N, cons
 
 int train_complex(gple_ctx* ctx, const double* X_, const double* y_, size_t N, const double* theta, unsigned flags, gple_model** out_model, gple_complex_scalars* out)
 {
-	gpr_setup_attributes();
 	DeviceArray<double> X(ctx, X_, 2 * N, false), y(ctx, y_, 2 * N, false);
 	gple_model* m = new gple_model();
 	m->owner = ctx;
@@ -1388,7 +1371,6 @@ int train_complex(gple_ctx* ctx, const double* X_, const double* y_, size_t N, c
 ///    remaining queries, so the GEMM always runs at full occupancy.
 void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size_t Q, const double* d_yq, double* d_pred, double* d_var, double* d_cut, double* d_err)
 {
-	gpr_setup_attributes();
 	const int nb = m->is_complex ? 2 : 1;
 	const BlockSpec spec = m->is_complex ? complex_spec(m->theta) : real_spec(m->theta);
 	const long long total_rows = (long long)(Q)*nb;
@@ -1546,7 +1528,6 @@ int set_variance_gemm_variant(int variant)
 /// Times `iters` launches of one variant on synthetic operands (tuning / roofline helper)
 double bench_variance_gemm(gple_ctx* ctx, int variant, int rows, int n, int iters)
 {
-	gpr_setup_attributes();
 	double* A = ctx->ws.get<double>("pred.A", size_t(rows) * n);
 	double* W = ctx->ws.get<double>("bench.W", size_t(n) * n);
 	double* q = ctx->ws.get<double>("pred.q", size_t(rows) * MAX_VAR_SPLITS);

@@ -306,17 +306,16 @@ void markov_chains_device(gple_ctx* ctx, const gple_mc_source& src, double* d_pt
 	}
 }
 
+void mc_setup_attributes()
+{
+	GPLE_CUDA(cudaFuncSetAttribute(autocorrelation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+}
+
 void chain_autocorrelation_device(gple_ctx* ctx, const double* d_chains, const size_t n, const size_t len, double* d_out)
 {
 	if (len * sizeof(double2) > 200 * 1024)
 	{
 		throw ArgError{"gple_chain_autocorrelation: chains longer than 12800 states do not fit in shared memory"};
-	}
-	static bool attr_done = false;
-	if (!attr_done)
-	{
-		GPLE_CUDA(cudaFuncSetAttribute(autocorrelation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-		attr_done = true;
 	}
 	const int half = int(len / 2);
 	double* part = ctx->ws.get<double>("mc.autocor", n * size_t(half));

@@ -39,6 +39,18 @@ def evolve(model: int, density, mass: float, dt: float, kernels, ctx=None):
     return outs
 
 
+def evolve_sharded(model: int, density, mass: float, dt: float, kernels, ctx=None):
+    """evolve() on G GPUs (one process each): `density` holds the FULL point sets on every rank; every rank evolves its own block
+    and the blocks are all-gathered in place inside the library (gple_evolve_sharded).  Returns the full evolved sets."""
+    ctx = ctx or L.default_context()
+    outs = [np.zeros((0, 4)) if a is None else L.f64(a).copy() for a in density]
+    ctx.check(ctx.lib.gple_evolve_sharded(ctx.h, int(model), _h(kernels[0]), _h(kernels[1]), _h(kernels[2]),
+                                          L.addr(outs[0]) if len(outs[0]) else None, len(outs[0]),
+                                          L.addr(outs[1]) if len(outs[1]) else None, len(outs[1]),
+                                          L.addr(outs[2]) if len(outs[2]) else None, len(outs[2]), float(mass), float(dt)))
+    return outs
+
+
 def new_point_predict(model: int, r, mass: float, dt: float, kernels, row: int, col: int, ctx=None):
     """new_point_predict() (evolve.cpp:425-443) for n points r (n, 2); returns complex (n,)."""
     ctx = ctx or L.default_context()

@@ -34,7 +34,8 @@ extern "C"
 		GPLE_ERR_ARG = 1,	  /* bad argument (null pointer, zero size, wrong model kind) */
 		GPLE_ERR_NOT_SPD = 2, /* factorisation met a non-positive pivot; scalars are NaN */
 		GPLE_ERR_CUDA = 3,	  /* CUDA runtime failure, see gple_last_error */
-		GPLE_ERR_STATE = 4	  /* quantity was not computed for this model (flag missing) */
+		GPLE_ERR_STATE = 4,	  /* quantity was not computed for this model (flag missing) */
+		GPLE_ERR_COMM = 5	  /* NCCL failure or NCCL not loadable (multi-GPU entry points only), see gple_last_error */
 	};
 
 	/* flags of gple_train_*: the three booleans of TrainingKernel's constructor (gple/kernel.h:128-134) */
@@ -96,12 +97,12 @@ extern "C"
 	/* Replaces ComplexKernelBase::ComplexKernelBase (gple/complex_kernel.cpp:134-200).
 	 * theta = (sigma, sigma_R, l_Rx, l_Rp, sigma_I, l_Ix, l_Ip, sigma_n) (complex_kernel.cpp:230-256).
 	 * K_out: nL x nR real; Kt_out: nL x nR complex (pseudo-covariance). */
+	int gple_kernel_complex(gple_ctx* ctx, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[8], int same_set, double* K_out, double* Kt_out);
 	/* calculate_derivative / calculate_pseudo_derivative of the complex kernel (gple/complex_kernel.cpp:20-59, 74-132), materialised:
 	 * dK_out = 8 real nL x nR matrices, dKt_out = 8 complex ones (either may be NULL), parameter order sigma, sigma_R, l_Rx, l_Rp,
 	 * sigma_I, l_Ix, l_Ip, sigma_n, column-major.  The training path never stores them (it works in composite form); this entry
 	 * exists for the getters / parity with the reference's derivative arrays, quirk q2 included. */
 	int gple_kernel_complex_derivatives(gple_ctx* ctx, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[8], int same_set, double* dK_out, double* dKt_out);
-	int gple_kernel_complex(gple_ctx* ctx, const double* XL, size_t nL, const double* XR, size_t nR, const double theta[8], int same_set, double* K_out, double* Kt_out);
 
 	/* ---- training ----------------------------------------------------------------------------------
 	 * Replaces TrainingKernel::TrainingKernel (gple/kernel.cpp:244-479) and its getters (kernel.h:136-243).
@@ -184,6 +185,32 @@ extern "C"
 	 * from the 9 backward-propagated predictions per point (evolve.cpp:184-372).  A NULL model means the
 	 * element has no predictor (predicts 0, main.cpp:85-99).  Points are updated in place. */
 	int gple_evolve(gple_ctx* ctx, int pes_model, const gple_model* m00, const gple_model* m10, const gple_model* m11, double* pts00, size_t n00, double* pts10, size_t n10, double* pts11, size_t n11, double mass, double dt);
+
+	/* ---- multi-GPU: one process per GPU, one NCCL communicator per context ----------------
+	 * The path shards over the evolved points; a factorisation never spans GPUs.  The reference's tick
+	 * (gple/main.cpp:140-141, 176) evolves every point and then rebuilds the element models from ALL evolved points
+	 * (predict.cpp:246-280), so the one exchange per step is the all-gather of the evolved (r, rho) sets, after which
+	 * every rank holds the full sets and rebuilds its models redundantly (BASELINE.json north_star).
+	 * Bootstrap: rank 0 calls gple_comm_unique_id and hands the 128 bytes to the other ranks by whatever channel the host
+	 * has (MPI, a torch.distributed store, a file); every rank then calls gple_ctx_comm_init on its context.
+	 * NCCL is bound at run time (libnccl.so.2); without it these entry points return GPLE_ERR_COMM and nothing else changes. */
+#define GPLE_COMM_ID_BYTES 128
+	int gple_comm_unique_id(unsigned char id[GPLE_COMM_ID_BYTES]);
+	int gple_ctx_comm_init(gple_ctx* ctx, int rank, int nranks, const unsigned char id[GPLE_COMM_ID_BYTES]);
+	/* rank / size of the context's communicator; (0, 1) for a context without one */
+	int gple_ctx_comm_info(const gple_ctx* ctx, int* rank, int* nranks);
+	/* the block [lo, hi) of `total` records that `rank` owns (blocks differ by at most one record) */
+	int gple_partition(size_t total, int rank, int nranks, size_t* lo, size_t* hi);
+	/* In-place all-gather of a block-partitioned point set: pts = the FULL array of `total` PhaseSpacePoints (host or
+	 * device) of which this rank's block is valid on entry; all blocks are valid on return.  ncclAllGather on the context
+	 * stream (grouped ncclBroadcast when the blocks are uneven).  A no-op on a context without a communicator. */
+	int gple_allgather_points(gple_ctx* ctx, double* pts, size_t total);
+	/* sum over the ranks of `count` doubles, in place (partial sums of gple_observables / gple_validation_error over sharded points) */
+	int gple_allreduce_sum(gple_ctx* ctx, double* values, size_t count);
+	/* gple_evolve over point sets that are block-partitioned over the ranks: pts?? are the FULL sets (n?? = their full sizes);
+	 * every rank evolves its own block of each element and the blocks are all-gathered in place, so that every rank returns
+	 * with the full evolved sets -- evolve(density) of main.cpp:140 on G GPUs.  Identical to gple_evolve without a communicator. */
+	int gple_evolve_sharded(gple_ctx* ctx, int pes_model, const gple_model* m00, const gple_model* m10, const gple_model* m11, double* pts00, size_t n00, double* pts10, size_t n10, double* pts11, size_t n11, double mass, double dt);
 
 	/* Replaces new_point_predict() (gple/evolve.cpp:425-443) for n phase points r of element (row, col):
 	 * out = n complex densities. */
