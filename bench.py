@@ -55,38 +55,65 @@ def make_inputs():
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the reference timed on the host cores, bounded sample
+# reference arm / cpu_baseline: the reference's own CPU implementation timed on the host cores, bounded sample
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_sample(sets):
-    """One bounded sample of the C2 step on the CPU (oracle = port of the reference's Eigen/CPU implementation).
+def cpu_backend():
+    """oracle/_ref (the reference's unmodified translation units, compiled in the build container and shipped with the
+    snapshot) when present, else the oracle restatement.  Returns (module, kind)."""
+    try:
+        from oracle import ref
 
-    Measured: real-element TrainingKernel at N=2048; 128 real single-model predictions at N=2048;
-    TrainingComplexKernel at N=1024 (x8 for the N^3 scaling to 2048); 32 complex predictions at N=1024 (x4, N^2).
-    Returns (seconds per full step, description).
-    """
+        if ref.available():
+            return ref, "reference"
+    except Exception:
+        pass
     from oracle import oracle as orc
 
-    t = time.perf_counter()
-    k0 = orc.TrainingKernel(THETA_R, sets[0][0], sets[0][1], True, True, False)
-    t_train_real = time.perf_counter() - t
-    Xq, _ = syn.extra_points(3, 0, sets[0][0], 128, CENTRE)
-    t = time.perf_counter()
-    k0.predict(Xq)
-    t_q_real = (time.perf_counter() - t) / len(Xq)
-    nc = 1024
-    t = time.perf_counter()
-    k1 = orc.TrainingComplexKernel(THETA_C, sets[1][0][:nc], sets[1][1][:nc], True, True, False)
-    t_train_cplx = (time.perf_counter() - t) * (N_TRAIN / nc) ** 3
-    Xq, _ = syn.extra_points(3, 1, sets[1][0], 32, CENTRE)
-    t = time.perf_counter()
-    k1.predict(Xq)
-    t_q_cplx = (time.perf_counter() - t) / len(Xq) * (N_TRAIN / nc) ** 2
-    queries = 8 * Q_POINTS
-    step_s = 2 * t_train_real + t_train_cplx + 2 * queries * t_q_real + queries * t_q_cplx
-    desc = (f"oracle port, {orc.num_threads()} threads: real train N=2048 measured ({t_train_real:.2f}s), 128 real queries N=2048 "
-            f"({t_q_real * 1e3:.2f} ms/query), complex train N=1024 x8 ({t_train_cplx:.1f}s), 32 complex queries N=1024 x4 "
-            f"({t_q_cplx * 1e3:.2f} ms/query); step = 2 real + 1 complex train + 8Q queries per predictor, extrapolated")
-    return step_s, desc, orc.num_threads()
+    return orc, "port"
+
+
+class CpuStep:
+    """The bench step on the CPU, through the reference's own functions, as a bounded sample.
+
+    Full-size and timed ONCE: the TrainingKernels rebuild of the step (TrainingKernel x 2 and TrainingComplexKernel at the
+    workload's N; kernel.cpp:244-335, complex_kernel.cpp:221-377).  Timed per sample(): evolve() (evolve.cpp:377-423) of
+    `points` phase-space points per element over those three models -- the same 9 back-propagated predictions per point the
+    GPU step makes -- which is EXTRAPOLATED linearly to the Q points per element of the workload (points are independent:
+    evolve.cpp:392-420 is a par_unseq loop over them)."""
+
+    def __init__(self, sets, points=16):
+        from oracle import oracle as orc
+
+        self.mod, self.kind = cpu_backend()
+        self.cores = orc.num_threads()
+        self.points = points
+        m = self.mod
+        t = time.perf_counter()
+        k0 = m.TrainingKernel(THETA_R, sets[0][0], sets[0][1], True, True, False)
+        self.t_real = time.perf_counter() - t
+        t = time.perf_counter()
+        k1 = m.TrainingComplexKernel(THETA_C, sets[1][0], sets[1][1], True, True, False)
+        self.t_cplx = time.perf_counter() - t
+        k2 = m.TrainingKernel(THETA_R, sets[2][0], sets[2][1], True, True, False)
+        self.models = [k0, k1, k2]
+        self.pts = [syn.points_aos(*s) for s in sets]
+        self.calls = 0
+
+    def sample(self):
+        """seconds of one full step, extrapolated from `points` evolved points per element"""
+        lo = (self.calls * self.points) % (N_TRAIN - self.points)
+        self.calls += 1
+        pts = [p[lo:lo + self.points].copy() for p in self.pts]
+        t = time.perf_counter()
+        self.mod.evolve(PES_MODEL, pts[0], pts[1], pts[2], syn.MASS, syn.DT, *self.models)
+        self.t_evolve = time.perf_counter() - t
+        return 2 * self.t_real + self.t_cplx + self.t_evolve * (Q_POINTS / self.points)
+
+    def describe(self):
+        what = "oracle/_ref = the reference's own translation units compiled unmodified (stand-in Eigen/xtensor headers, host OpenBLAS for MKL)" if self.kind == "reference" else "oracle port of the reference (oracle/_ref not present)"
+        return (f"{what}, {self.cores} threads: TrainingKernel N={N_TRAIN} measured once ({self.t_real:.2f} s, counted twice), TrainingComplexKernel N={N_TRAIN} measured once "
+                f"({self.t_cplx:.1f} s), evolve() of {self.points} points/element over the three models measured per sample ({self.t_evolve:.2f} s) and "
+                f"extrapolated x{Q_POINTS // self.points} to Q={Q_POINTS} points/element")
 
 
 def cpu_best_effort_sample(sets):
@@ -121,9 +148,10 @@ def run_reference(args):
     if rank != 0:
         return
     sets = [syn.training_set(2, e, N_TRAIN, CENTRE) for e in range(3)]
-    times, desc, cores = [], "", 1
+    cpu = CpuStep(sets)
+    times = []
     for i in range(args.warmup + args.steps):
-        s, desc, cores = cpu_sample(sets)
+        s = cpu.sample()
         if i >= args.warmup:
             times.append(s)
     step_s = float(np.mean(times))
@@ -131,8 +159,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference cannot be compiled here (Eigen/NLopt/xtensor/MKL/TBB absent); CPU restatement timed"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "extrapolated": True,
+        "config": {"workload": WORKLOAD, "note": "CPU arm: every step is a bounded sample of the workload (see cpu_baseline.sample); the full step would take hours"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe(), "extrapolated": True},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -167,6 +196,81 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": reasons}
+
+
+def north_star_extra(ctx, dev, dmma_peak, q_points, steps):
+    """BASELINE.json north_star on ONE GPU: a full time step at N = 16384 training points and 1e6 evolved MC points (configs[4]
+    largest size).  State: the reference's t = 0 state (only rho00 populated, gple/main.cpp:57-64): the step trains one real
+    element at N = 16384 (kernel build + factorise + inverse + LOOCV error + averages) and evolves 1e6 points (2 GPR queries
+    per point into that model).  Timed like the headline: CUDA events around the whole step, inputs resident, bound-gated
+    variance on (product default) and, once, off (every variance computed = the reference's amount of work).
+    FP64 fraction = executed tensor-core flops (factorise 2n^3/3 + inverse, variance GEMM rows*n*(n+128)) / step time / DMMA peak:
+    everything that is not a DMMA flop (kernel build, mean pass, reductions, launch gaps) counts against it."""
+    import ctypes as C
+
+    import torch
+
+    from gaussian_process_liouville_equation_b200 import _lib as L
+    from gaussian_process_liouville_equation_b200 import kernel as gk
+
+    lib = ctx.lib
+    N = 16384
+    th = np.ascontiguousarray(syn.theta_real(max(0.25, (2048.0 / N) ** 0.5)))  # lengths shrink with N: cond(K) comparable to C2 (allowed by opt.cpp:1036-1040)
+    X, y = syn.training_set(90, 0, N, CENTRE)
+    Xe, ye = syn.extra_points(90, 0, X, q_points, CENTRE)
+    d_X = torch.from_numpy(X).to(dev)
+    d_y = torch.from_numpy(np.ascontiguousarray(y).view(np.float64)).to(dev)
+    pts0 = torch.from_numpy(syn.points_aos(Xe, ye)).to(dev)
+    scal = L.RealScalars()
+
+    def step(q):
+        pts = pts0[:q].clone()
+        torch.cuda.synchronize()
+        for slot in range(4):
+            ctx.profile_read(slot)
+        ctx.gate_statistics()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        h = C.c_void_p()
+        ctx.check(lib.gple_train_real(ctx.h, d_X.data_ptr(), d_y.data_ptr(), N, L.addr(th), L.CALC_ERROR | L.CALC_AVERAGE, C.byref(h), C.byref(scal)))
+        ctx.check(lib.gple_evolve(ctx.h, PES_MODEL, h, None, None, pts.data_ptr(), q, None, 0, None, 0, syn.MASS, syn.DT))
+        e1.record()
+        torch.cuda.synchronize()
+        lib.gple_model_destroy(ctx.h, h)
+        return e0.elapsed_time(e1), [ctx.profile_read(slot) for slot in range(4)], ctx.gate_statistics()
+
+    ctx.profile_enable(True)
+    out = {"workload": f"north star / C5: Tully SAC t=0 state (rho00 populated), N={N} training points, Q={q_points} evolved MC points; step = TrainingKernel rebuild + evolve (2Q GPR predictions)",
+           "n_train": N, "q_points": q_points, "dmma_peak_tflops": dmma_peak}
+    for gated in (True, False):
+        ctx.set_gated_variance(gated)
+        step(q_points if gated else min(q_points, 20000))  # warm-up at the steady-state buffer sizes
+        runs = [step(q_points) for _ in range(steps if gated else 1)]
+        ms = float(np.mean([r[0] for r in runs]))
+        prof, gs = runs[-1][1], runs[-1][2]
+        flops = prof[0][2] + prof[2][2]
+        ref_flops = float(N) ** 3 + 4.0 * q_points * float(N) ** 2  # SURVEY.md 8d: reference formulation (LDLT + inverse ~ N^3, 2 Q queries x 2 N^2)
+        out["gated" if gated else "every_variance_computed"] = {
+            "ms_per_step": ms, "steps_per_s": 1000.0 / ms, "steps_timed": len(runs), "executed_dmma_tflop": flops / 1e12, "whole_step_tflops": flops / ms / 1e9,
+            "frac_of_fp64_peak": flops / ms / 1e9 / dmma_peak, "reference_formulation_tflops_equiv": ref_flops / ms / 1e9,
+            "variance_gemm_tflops": prof[0][2] / max(prof[0][0], 1e-9) / 1e9, "factorise_ms": prof[2][0], "factorise_tflops": prof[2][2] / max(prof[2][0], 1e-9) / 1e9,
+            "kernel_build_ms": prof[1][0], "mean_pass_ms": prof[3][0], "rows_through_variance_gemm_fraction": (gs[1] / gs[0]) if gated and gs[0] else 1.0}
+    ctx.set_gated_variance(True)
+    ctx.profile_enable(False)
+    del pts0
+    # parity spot-check at this size through the reference-shaped API: K (K^-1 y) = y, and the LOOCV identity
+    # error = sum_i (v_i / [K^-1]_ii)^2 (kernel.cpp:285-287) against the explicit inverse
+    k = gk.TrainingKernel(th, (X, y), True, True, False, ctx=ctx)
+    v, lab = k.get_inverse_times_label(), k.get_label()
+    K = gk.kernel_matrix(X, X, th, True, ctx=ctx)
+    Kinv = k.get_inverse()
+    probe = np.random.default_rng(16384).standard_normal((N, 4))
+    out["check"] = {"status": int(k.status), "population": k.get_population(), "loocv_error": k.get_error(),
+                    "residual_K_v_minus_y_rel": float(np.abs(K @ v - lab).max() / np.abs(lab).max()),
+                    "loocv_identity_rel": float(abs(k.get_error() / float(np.sum((v / np.diag(Kinv)) ** 2)) - 1.0)),
+                    "K_Kinv_probe_rel": float(np.abs(K @ (Kinv @ probe) - probe).max() / np.abs(probe).max())}
+    k.close()
+    return out
 
 
 def run_ours(args):
@@ -365,9 +469,15 @@ def run_ours(args):
                   "reference_formulation_tflops_equiv": alg_flops_step / ((full_ms / args.steps) * 1e-3) / 1e12,
                   "check": last_scalars},
     }
+    if world == 1 and not args.no_north_star:
+        pool.shutdown()
+        del flush, d_pts, d_pts0
+        torch.cuda.empty_cache()
+        line["extra"]["north_star"] = north_star_extra(ctx, dev, dmma_peak, args.north_star_points, 2)
     if world == 1 and not args.no_cpu_baseline:
-        step_s, desc, cores = cpu_sample(sets)
-        line["cpu_baseline"] = {"value": 1.0 / step_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        cpu = CpuStep(sets)
+        step_s = cpu.sample()
+        line["cpu_baseline"] = {"value": 1.0 / step_s, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe(), "extrapolated": True}
         try:  # second CPU number of SURVEY.md 8d: best effort on the host's BLAS / LAPACK (reported, not the reference arm)
             be_s, be_desc = cpu_best_effort_sample(sets)
             line["cpu_baseline"]["best_effort_blas"] = {"value": 1.0 / be_s, "unit": UNIT, "sample": be_desc}
@@ -386,6 +496,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-north-star", action="store_true", help="skip extra.north_star (N=16384, 1e6 evolved points; about 40 s)")
+    ap.add_argument("--north-star-points", type=int, default=1_000_000)
     ap.add_argument("--gate-stage-tiles", type=int, default=None, help="override GPLE_OPT_GATE_STAGE_TILES (tuning)")
     ap.add_argument("--gate-stage-tiles-im", type=int, default=-1, help="override GPLE_OPT_GATE_STAGE_TILES_IM (tuning)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2 (default, BASELINE.json configs[1]); c4 = configs[3]: ECR, N=4096, 1e6 evolved points/element, meant for --gpus 8")
@@ -398,7 +510,7 @@ def main():
         THETA_C = THETA_C * np.array([1, 1, scale, scale, 1, scale, scale, 1])
         WORKLOAD = ("C4: Tully extended coupling with reflection, N=4096 training points/element, 3 elements, Q=1e6 evolved MC points/element/step "
                     "sharded over the GPUs; step = TrainingKernels rebuild (3 elements) + evolve (8Q GPR predictions per element)")
-        args.no_cpu_baseline = True  # the CPU sample is sized for C2
+        args.no_cpu_baseline = args.no_north_star = True  # the CPU sample is sized for C2
     if args.impl == "reference":
         run_reference(args)
     else:

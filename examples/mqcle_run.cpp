@@ -6,9 +6,17 @@
 // (the quantities of output_average / spdlog in main.cpp:117-126) and a summary.
 //
 //   mqcle_run N ticks reopt_freq pes_model(0 SAC, 1 DAC, 2 ECR) [seed] [x0]
+//
+// Multi-GPU (one process per GPU): start G copies with GPLE_RANK = 0 .. G-1, GPLE_WORLD_SIZE = G,
+// GPLE_COMM_FILE = a path all of them see (rank 0 publishes the NCCL id there) and GPLE_LOCAL_DEVICE = the GPU of the copy
+// (torchrun's RANK / WORLD_SIZE / LOCAL_RANK are understood as well).  Every rank runs the same loop on the same seeds;
+// evolve() moves only the rank's block of each point set and all-gathers the evolved sets through the library
+// (gple_evolve_sharded), so every rank rebuilds its models from the full sets exactly like main.cpp:140-141, 176.  The
+// "hash" lines (FNV-1a over the bytes of all points after the tick) are identical for every G.
 #include "../gaussian_process_liouville_equation_b200/host/gple_mc.hpp"
 
 #include <chrono>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 
@@ -29,6 +37,32 @@ int main(int argc, char** argv)
 	const double mass = 2000.0, dt = 1.0, sp = 0.7056, sx = 1.0 / (2.0 * sp);
 	const ClassicalPhaseVector r0{argc > 6 ? std::atof(argv[6]) : -10.0, 14.112}, SigmaR0{sx, sp};
 	std::mt19937_64 engine(seed);
+	auto env = [](const char* a, const char* b) -> const char*
+	{
+		const char* v = std::getenv(a);
+		return v != nullptr ? v : std::getenv(b);
+	};
+	const int rank = env("GPLE_RANK", "RANK") != nullptr ? std::atoi(env("GPLE_RANK", "RANK")) : 0;
+	const int world = env("GPLE_WORLD_SIZE", "WORLD_SIZE") != nullptr ? std::atoi(env("GPLE_WORLD_SIZE", "WORLD_SIZE")) : 1;
+	const int local = env("GPLE_LOCAL_DEVICE", "LOCAL_RANK") != nullptr ? std::atoi(env("GPLE_LOCAL_DEVICE", "LOCAL_RANK")) : 0;
+	Context::device() = local;
+	if (world > 1)
+	{
+		const char* file = std::getenv("GPLE_COMM_FILE");
+		if (file == nullptr)
+		{
+			std::fprintf(stderr, "mqcle_run: GPLE_COMM_FILE is not set\n");
+			return 2;
+		}
+		Context::init_distributed(rank, world, file, local);
+	}
+	if (rank != 0)
+	{
+		if (std::freopen("/dev/null", "w", stdout) == nullptr) // rank 0 reports; the others compute the same numbers
+		{
+			return 2;
+		}
+	}
 	const auto begin = std::chrono::steady_clock::now();
 
 	// main.cpp:36-57: N copies of r0, then the Metropolis walk in the initial distribution
@@ -56,6 +90,22 @@ int main(int argc, char** argv)
 	{
 		const QuantumVectorD E = calculate_total_energy_average_each_surface(density, mass, pes_model);
 		std::printf("tick %zu %.15e %.15e %.15e\n", tick, all_kernels->calculate_population(), all_kernels->calculate_total_energy_average(E), all_kernels->calculate_purity());
+	};
+	auto hash_points = [&](const std::size_t tick)
+	{
+		std::uint64_t h = 1469598103934665603ull;
+		for (const AllPoints* set : {&density, &extra_points})
+		{
+			for (const ElementPoints& pts : *set)
+			{
+				const unsigned char* b = reinterpret_cast<const unsigned char*>(pts.data());
+				for (std::size_t i = 0; i < pts.size() * sizeof(PhaseSpacePoint); i++)
+				{
+					h = (h ^ b[i]) * 1099511628211ull;
+				}
+			}
+		}
+		std::printf("hash%zu %u %u\n", tick, unsigned(h & 0xffffffffu), unsigned(h >> 32));
 	};
 	output(0);
 	std::printf("displacement %.17g\nmc_steps %zu\n", MCParams[0].get_max_displacement(), MCParams[0].get_num_MC_steps());
@@ -110,9 +160,10 @@ int main(int argc, char** argv)
 			}
 		}
 		output(iTick);
+		hash_points(iTick);
 	}
 	const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - begin).count();
-	std::printf("elements %zu %zu %zu\noptimisations %zu\nwall_s %.3f\n", density[0].size(), density[1].size(), density[2].size(), optimisations, wall);
+	std::printf("ranks %d\nelements %zu %zu %zu\noptimisations %zu\nwall_s %.3f\n", Context::num_ranks(), density[0].size(), density[1].size(), density[2].size(), optimisations, wall);
 	std::printf("seconds_evolve_second_half %.4f\nticks_second_half %zu\n", t_evolve_late, late_ticks);
 	std::printf("seconds_evolve %.4f\nseconds_rebuild %.4f\nseconds_optimise_in_loop %.4f\nseconds_new_element_selection %.4f\n", t_evolve, t_rebuild, t_opt, t_select);
 	return 0;

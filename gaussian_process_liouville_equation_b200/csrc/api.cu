@@ -322,6 +322,11 @@ extern "C"
 			ctx->gated_variance = value != 0;
 			return GPLE_OK;
 		}
+		if (option == GPLE_OPT_REFINE_SOLUTION)
+		{
+			ctx->refine_solution = value != 0;
+			return GPLE_OK;
+		}
 		if (option == GPLE_OPT_GATE_STAGE_TILES && value >= -1)
 		{
 			ctx->gate_stage_tiles = value;

@@ -142,6 +142,7 @@ struct gple_ctx
 	int num_sms = 148;
 	// bound-gated variance (GPLE_OPT_GATED_VARIANCE) and its statistics
 	bool gated_variance = true;
+	bool refine_solution = true; // GPLE_OPT_REFINE_SOLUTION
 	int gate_stage_tiles = -1;	  // GPLE_OPT_GATE_STAGE_TILES (-1: automatic)
 	int gate_stage_tiles_im = -1; // GPLE_OPT_GATE_STAGE_TILES_IM (-1: automatic)
 	unsigned long long gate_rows_total = 0, gate_rows_variance = 0, gate_rows_zero = 0, gate_rows_stage_b = 0;

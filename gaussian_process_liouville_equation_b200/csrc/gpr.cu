@@ -768,6 +768,60 @@ __global__ void __launch_bounds__(128) col_pass_kernel(const double* __restrict_
 	p[n + k] = ss;
 	p[2 * n + k] = sc;
 }
+
+/// Residual of the solve, r = y' - C v, with the covariance regenerated from the points (the factorisation overwrote it):
+/// one warp per composite row, entries evaluated exactly as build_cov_lower_kernel evaluates them.  One step of iterative
+/// refinement v <- v + W^T W r brings K^-1 y' from the accuracy of the explicit triangular inverse (a few 1e-8 relative at
+/// cond(K) ~ 1e7, measured against a double-double evaluation, tests/golden/arbiter_dd.cpp) to that of a backward-stable solve
+/// (1e-10), which is what the reference's LDLT + solve delivers (kernel.cpp:281-284).
+__global__ void __launch_bounds__(256) residual_kernel(const BlockSpec spec, const double2* __restrict__ X, const int N, const int Np, const int n, const double* __restrict__ label, const double* __restrict__ v, double* __restrict__ r)
+{
+	const int I = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+	if (I >= n)
+	{
+		return;
+	}
+	const int rb = I / Np, i = I - rb * Np;
+	double acc = 0.0;
+	if (i < N)
+	{
+		const double2 xi = X[i];
+		for (int cb = 0; cb < spec.nb; cb++)
+		{
+			const GaussBlock g = spec.b[rb][cb];
+			const double* __restrict__ vb = v + cb * Np;
+			for (int j = lane; j < N; j += 32)
+			{
+				const double val = gauss_value(g, xi, X[j]) + (i == j ? g.diag_add : 0.0);
+				acc = fma(-val, vb[j], acc);
+			}
+		}
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	}
+	if (lane == 0)
+	{
+		r[I] = i < N ? label[I] + acc : 0.0;
+	}
+}
+/// v += sum over the slabs of the solution partials of a column pass
+__global__ void refine_add_kernel(const double* __restrict__ part, const int n, const int slabs, double* __restrict__ v)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n)
+	{
+		return;
+	}
+	double a = 0.0;
+	for (int s = 0; s < slabs; s++)
+	{
+		a += part[size_t(s) * 3 * n + k];
+	}
+	v[k] += a;
+}
 __global__ void col_reduce_kernel(const double* __restrict__ part, const int n, const int slabs, double* __restrict__ v, double* __restrict__ ss, double* __restrict__ cross)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1137,6 +1191,15 @@ int train_common(gple_ctx* ctx, gple_model* m, const BlockSpec& spec, const Devi
 	double* part = ctx->ws.get<double>("train.colpart", size_t(nslab) * 3 * n);
 	GPLE_LAUNCH(ctx, col_pass_kernel, dim3(n / 128, nslab), 128, 0, m->W, n, Np, m->is_complex, z, slab, part);
 	GPLE_LAUNCH(ctx, col_reduce_kernel, (n + 255) / 256, 256, 0, part, n, nslab, m->v, m->kinv_diag, m->is_complex ? m->kinv_diag + n : nullptr);
+	if (ctx->refine_solution)
+	{
+		// one step of iterative refinement of v = K^-1 y' (see residual_kernel)
+		double* r = ctx->ws.get<double>("train.r", size_t(n));
+		GPLE_LAUNCH(ctx, residual_kernel, (n + 7) / 8, 256, 0, spec, reinterpret_cast<const double2*>(m->X), N, Np, n, m->label, m->v, r);
+		GPLE_LAUNCH(ctx, trmv_lower_kernel, (n + 7) / 8, 256, 0, m->W, n, r, z);
+		GPLE_LAUNCH(ctx, col_pass_kernel, dim3(n / 128, nslab), 128, 0, m->W, n, Np, 0, z, slab, part);
+		GPLE_LAUNCH(ctx, refine_add_kernel, (n + 255) / 256, 256, 0, part, n, nslab, m->v);
+	}
 	int h_info = 0;
 	GPLE_CUDA(cudaMemcpyAsync(&h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 	GPLE_CUDA(cudaStreamSynchronize(ctx->stream));

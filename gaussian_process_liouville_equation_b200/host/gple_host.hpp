@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <array>
 #include <cassert>
+#include <chrono>
+#include <cstdio>
 #include <complex>
 #include <condition_variable>
 #include <functional>
@@ -72,10 +74,85 @@ public:
 		static thread_local int s = 0;
 		return s;
 	}
-	static gple_ctx* get(int device = 0)
+	/// RAII: slot 0 for the calling thread within a scope
+	struct ContextSlot0
 	{
-		static Context c(device);
+		int previous;
+		ContextSlot0(): previous(slot()) { slot() = 0; }
+		~ContextSlot0() { slot() = previous; }
+	};
+	/// device of this process (one process per GPU): set before the first use of the library, default 0
+	static int& device()
+	{
+		static int d = 0;
+		return d;
+	}
+	static gple_ctx* get()
+	{
+		static Context c(device());
 		return c.ctx[slot()];
+	}
+	/// Multi-GPU (one process per GPU): gives the main context (slot 0) its NCCL communicator.  Rank 0 draws
+	/// the unique id and publishes it in `id_file` (any path all ranks see: a shared directory of the job); the others
+	/// wait for it.  A launcher that has its own channel (MPI_Bcast) can call gple_comm_unique_id / gple_ctx_comm_init itself.
+	/// After this, evolve() shards the points over the ranks and all-gathers the evolved sets (gple_evolve_sharded).
+	static void init_distributed(const int rank, const int nranks, const std::string& id_file, const int local_device)
+	{
+		device() = local_device;
+		unsigned char id[GPLE_COMM_ID_BYTES];
+		if (rank == 0)
+		{
+			check(gple_comm_unique_id(id), "gple_comm_unique_id");
+			const std::string tmp = id_file + ".tmp";
+			std::FILE* f = std::fopen(tmp.c_str(), "wb");
+			if (f == nullptr || std::fwrite(id, 1, sizeof(id), f) != sizeof(id))
+			{
+				throw std::runtime_error("init_distributed: cannot write " + tmp);
+			}
+			std::fclose(f);
+			std::rename(tmp.c_str(), id_file.c_str()); // atomic: a reader never sees a partial id
+		}
+		else
+		{
+			for (int tries = 0;; tries++)
+			{
+				std::FILE* f = std::fopen(id_file.c_str(), "rb");
+				if (f != nullptr)
+				{
+					const std::size_t got = std::fread(id, 1, sizeof(id), f);
+					std::fclose(f);
+					if (got == sizeof(id))
+					{
+						break;
+					}
+				}
+				if (tries > 6000)
+				{
+					throw std::runtime_error("init_distributed: no communicator id in " + id_file + " after 60 s");
+				}
+				std::this_thread::sleep_for(std::chrono::milliseconds(10));
+			}
+		}
+		const ContextSlot0 main_slot;
+		check(gple_ctx_comm_init(get(), rank, nranks, id), "gple_ctx_comm_init");
+	}
+	static int rank()
+	{
+		int r = 0;
+		gple_ctx_comm_info(main(), &r, nullptr);
+		return r;
+	}
+	static int num_ranks()
+	{
+		int n = 1;
+		gple_ctx_comm_info(main(), nullptr, &n);
+		return n;
+	}
+	/// the context of slot 0, whatever the calling thread's slot (it owns the communicator)
+	static gple_ctx* main()
+	{
+		const ContextSlot0 main_slot;
+		return get();
 	}
 	static void check(int rc, const char* where, bool allow_not_spd = false)
 	{
@@ -803,7 +880,7 @@ public:
 inline void evolve(AllPoints& density, double mass, double dt, const TrainingKernels& kernels, int pes_model)
 {
 	Context::check(
-		gple_evolve(Context::get(), pes_model, kernels.handle(0), kernels.handle(1), kernels.handle(2), reinterpret_cast<double*>(density[0].data()), density[0].size(), reinterpret_cast<double*>(density[1].data()), density[1].size(), reinterpret_cast<double*>(density[2].data()), density[2].size(), mass, dt),
+		gple_evolve_sharded(Context::main(), pes_model, kernels.handle(0), kernels.handle(1), kernels.handle(2), reinterpret_cast<double*>(density[0].data()), density[0].size(), reinterpret_cast<double*>(density[1].data()), density[1].size(), reinterpret_cast<double*>(density[2].data()), density[2].size(), mass, dt),
 		"evolve"
 	);
 }

@@ -81,7 +81,11 @@ extern "C"
 	{
 		GPLE_OPT_GATED_VARIANCE = 1,
 		GPLE_OPT_GATE_STAGE_TILES = 2,
-		GPLE_OPT_GATE_STAGE_TILES_IM = 3 /* complex element: blocks of Im rows in the stage (default -1 = a quarter of the Re blocks, at least 1) */
+		GPLE_OPT_GATE_STAGE_TILES_IM = 3, /* complex element: blocks of Im rows in the stage (default -1 = a quarter of the Re blocks, at least 1) */
+		/* (default 1) one step of iterative refinement of v = K^-1 y' after the factorisation (residual against the regenerated
+		 * covariance): v at the accuracy of the reference's LDLT solve (kernel.cpp:281-284) instead of that of the explicit
+		 * triangular inverse; 0 only for measuring the difference (tests/test_gpu_baseline_sizes.py) */
+		GPLE_OPT_REFINE_SOLUTION = 4
 	};
 	int gple_ctx_set_option(gple_ctx* ctx, int option, int value);
 	/* Gated predictions since the last call (then reset): out = {composite rows seen, rows sent through stage A of the

@@ -179,6 +179,25 @@ extern "C"
 		orc_evolve(pes_model, pts00, n00, pts10, n10, pts11, n11, mass, dt, handle(m00), handle(m10), handle(m11), nullptr);
 		return GPLE_OK;
 	}
+	// single-process mock of the multi-GPU entry points: a context without a communicator (rank 0 of 1)
+	int gple_comm_unique_id(unsigned char*) { return GPLE_ERR_COMM; }
+	int gple_ctx_comm_init(gple_ctx*, int, int, const unsigned char*) { return GPLE_ERR_COMM; }
+	int gple_ctx_comm_info(const gple_ctx*, int* rank, int* nranks)
+	{
+		if (rank != nullptr)
+		{
+			*rank = 0;
+		}
+		if (nranks != nullptr)
+		{
+			*nranks = 1;
+		}
+		return GPLE_OK;
+	}
+	int gple_evolve_sharded(gple_ctx* ctx, int pes_model, const gple_model* m00, const gple_model* m10, const gple_model* m11, double* pts00, size_t n00, double* pts10, size_t n10, double* pts11, size_t n11, double mass, double dt)
+	{
+		return gple_evolve(ctx, pes_model, m00, m10, m11, pts00, n00, pts10, n10, pts11, n11, mass, dt);
+	}
 	int gple_new_point_predict(gple_ctx*, int pes_model, const gple_model* m00, const gple_model* m10, const gple_model* m11, const double* r, size_t n, int row, int col, double mass, double dt, double* out)
 	{
 		orc_new_point_predict(pes_model, r, n, mass, dt, row, col, handle(m00), handle(m10), handle(m11), out);

@@ -86,3 +86,21 @@ def test_gpu_against_the_exact_values(oracle):
     for name, g, o in [("real " + n, d[n], do[n]) for n in d] + [("cplx " + n, dc[n], dco[n]) for n in dc]:
         print(f"  {name:16s} {g:9.2e} | {o:9.2e}")
         assert g <= max(50.0 * o, 1e-11), (name, g, o)
+
+
+def test_compiled_reference_against_the_exact_values_at_baseline_sizes():
+    """The reference's own outputs at N = 2048 / 4096 (gple_golden_ref_v1.npz, oracle/_ref) against the double-double arbiter
+    (gple_arbiter_dd_v1.npz, tests/golden/arbiter_dd.cpp, itself pinned to the mpmath arbiter at 2e-16): how far a
+    double-precision evaluation of the reference formulation is from its exact value at BASELINE.json's sizes.  The GPU
+    counterpart is tests/test_gpu_baseline_sizes.py."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    R = np.load(os.path.join(here, "golden", "gple_golden_ref_v1.npz"))
+    D = np.load(os.path.join(here, "golden", "gple_arbiter_dd_v1.npz"))
+    assert float(D["pin_distance_to_mpmath"]) < 5e-15
+    for tag in ("c2r", "c5r", "c2c"):
+        th = D[f"{tag}_theta"]
+        prior = th[0] ** 2 * (1 + th[3] ** 2) if len(th) == 4 else th[0] ** 2 * (th[1] ** 2 + th[4] ** 2 + th[7] ** 2)
+        d = dict(error=abs(R[f"{tag}_scalars"][1] / D[f"{tag}_error"] - 1), v=rel(R[f"{tag}_v"], D[f"{tag}_v"]), pred=rel(R[f"{tag}_pred"], D[f"{tag}_pred"]),
+                 var=float(np.abs(R[f"{tag}_var"] - D[f"{tag}_var"]).max() / prior), cutoff=rel(R[f"{tag}_cutoff"], D[f"{tag}_cutoff"]))
+        print(tag, d)
+        assert max(d["error"], d["pred"], d["var"], d["cutoff"]) <= 1e-9 and d["v"] <= 5e-9, (tag, d)
