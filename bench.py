@@ -30,7 +30,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from gaussian_process_liouville_equation_b200 import sharding  # noqa: E402
 from gaussian_process_liouville_equation_b200 import synthetic as syn  # noqa: E402
 
 N_TRAIN = 2048
@@ -296,6 +295,12 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     ctx = L.Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    if world > 1:
+        # multi-GPU through the library: the context gets its own NCCL communicator (gple_ctx_comm_init); torch.distributed only
+        # carries the 128-byte id to the other ranks and the barrier / max-over-ranks of the timing protocol
+        box = [L.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(rank, world, box[0])
     if args.gate_stage_tiles is not None:
         ctx.set_gate_stage_tiles(args.gate_stage_tiles, args.gate_stage_tiles_im)
     lib = ctx.lib
@@ -307,18 +312,19 @@ def run_ours(args):
     pool = ThreadPoolExecutor(3)
 
     sets, pts_all = make_inputs()
-    # block partition of the evolved points (strong scaling); every rank keeps the full training sets
-    lo, hi = sharding.partition(Q_POINTS, rank, world)
+    # block partition of the evolved points (strong scaling) inside gple_evolve_sharded: every rank holds the full point sets,
+    # evolves its own block of each and the blocks are all-gathered in place by the library (ncclAllGather on the context's
+    # stream); every rank keeps the full training sets
+    lo, hi = L.partition(Q_POINTS, rank, world)
     nloc = hi - lo
     thetas = [THETA_R, THETA_C, THETA_R]
     d_X = [torch.from_numpy(s[0]).to(dev) for s in sets]
     d_y = [torch.from_numpy(np.ascontiguousarray(s[1]).view(np.float64)).to(dev) for s in sets]
-    d_pts0 = [torch.from_numpy(p[lo:hi].copy()).to(dev) for p in pts_all]
+    d_pts0 = [torch.from_numpy(p).to(dev) for p in pts_all]
     d_pts = [t.clone() for t in d_pts0]
-    gathered = [None, None, None]
     h_X = [torch.from_numpy(s[0]).pin_memory() for s in sets]
     h_y = [torch.from_numpy(np.ascontiguousarray(s[1]).view(np.float64)).pin_memory() for s in sets]
-    h_pts0 = [torch.from_numpy(p[lo:hi].copy()).pin_memory() for p in pts_all]
+    h_pts0 = [torch.from_numpy(p).pin_memory() for p in pts_all]
     h_pts = [t.clone().pin_memory() for t in h_pts0]
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     last_scalars = {}
@@ -337,19 +343,26 @@ def run_ours(args):
             last_scalars[f"population{e}"] = s.population
         return h
 
+    # N > 1: the three element models are independent (predict.cpp:390-393), so each is trained on ONE rank -- the complex
+    # element (order 2N, ~8x the flops of a real one) on rank 0, the real ones on ranks 1 and 2 (both on rank 1 when there are
+    # only two) -- and replicated with gple_model_bcast; a factorisation never spans GPUs (BASELINE.json north_star)
+    owner = [1 % world, 0, 2 % world]
+
     def train_all(X, y):
         # gple_train_* returns after its stream is synchronised, so the models are complete when the threads join
-        return list(pool.map(lambda e: train_one(e, X, y), range(3)))
+        if world == 1:
+            return list(pool.map(lambda e: train_one(e, X, y), range(3)))
+        models = list(pool.map(lambda e: train_one(e, X, y) if owner[e] == rank else C.c_void_p(), range(3)))
+        for e in range(3):
+            ctx.check(lib.gple_model_bcast(ctx.h, C.byref(models[e]), owner[e]))
+        return models
 
     def step(X, y, pts):
         """One time step through the C-ABI.  X, y, pts: device tensors (resident run) or pinned host tensors (e2e run)."""
         models = train_all(X, y)
-        ctx.check(lib.gple_evolve(ctx.h, PES_MODEL, models[0], models[1], models[2], pts[0].data_ptr(), nloc, pts[1].data_ptr(), nloc, pts[2].data_ptr(), nloc, syn.MASS, syn.DT))
+        ctx.check(lib.gple_evolve_sharded(ctx.h, PES_MODEL, models[0], models[1], models[2], pts[0].data_ptr(), Q_POINTS, pts[1].data_ptr(), Q_POINTS, pts[2].data_ptr(), Q_POINTS, syn.MASS, syn.DT))
         for h in models:
             lib.gple_model_destroy(ctx.h, h)
-        if world > 1 and pts[0].is_cuda:
-            for e in range(3):
-                gathered[e] = sharding.all_gather_points(pts[e], Q_POINTS)
 
     def reset():
         for a, b in zip(d_pts, d_pts0):
@@ -384,11 +397,7 @@ def run_ours(args):
     resident = lambda: step(d_X, d_y, d_pts)  # noqa: E731
 
     def host_step():
-        step(h_X, h_y, h_pts)
-        if world > 1:  # the exchange of the evolved sets, from the host copies
-            for e in range(3):
-                d_pts[e].copy_(h_pts[e], non_blocking=True)
-                gathered[e] = sharding.all_gather_points(d_pts[e], Q_POINTS)
+        step(h_X, h_y, h_pts)  # host buffers in, full evolved sets back in the same host buffers (copies + exchange inside the call)
 
     for _ in range(max(args.warmup, 3)):
         reset()
@@ -447,7 +456,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "parallelism": f"points sharded over {world} GPU(s); models rebuilt redundantly; NCCL all-gather of evolved points",
+        "config": {"workload": WORKLOAD, "parallelism": f"evolved points block-partitioned over {world} GPU(s) inside gple_evolve_sharded; each element model trained on one rank and replicated (gple_model_bcast); one in-place NCCL all-gather of the evolved sets per element on the library's own communicator",
                    "l2": "512 MiB buffer written between timed steps; per-step working set (K* chunk 310-620 MB) exceeds L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -77,6 +77,7 @@ SIGNATURES = {
     "gple_ctx_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gple_partition": (C.c_int, [_sz, C.c_int, C.c_int, C.POINTER(_sz), C.POINTER(_sz)]),
     "gple_allgather_points": (C.c_int, [_vp, _dp, _sz]),
+    "gple_model_bcast": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.c_int]),
     "gple_allreduce_sum": (C.c_int, [_vp, _dp, _sz]),
     "gple_evolve_sharded": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, _dp, _sz, _dp, _sz, C.c_double, C.c_double]),
     "gple_new_point_predict": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _dp, _sz, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),

@@ -824,6 +824,19 @@ extern "C"
 			}
 		);
 	}
+	int gple_model_bcast(gple_ctx* ctx, gple_model** model, int root)
+	{
+		return guarded(
+			ctx,
+			[&]() -> int
+			{
+				require(model != nullptr && root >= 0 && root < ctx->comm_size, "gple_model_bcast: null model slot or bad root");
+				model_bcast(ctx, model, root);
+				sync(ctx);
+				return GPLE_OK;
+			}
+		);
+	}
 	int gple_evolve_sharded(gple_ctx* ctx, int pes_model, const gple_model* m00, const gple_model* m10, const gple_model* m11, double* pts00, size_t n00, double* pts10, size_t n10, double* pts11, size_t n11, double mass, double dt)
 	{
 		return guarded(

@@ -18,197 +18,459 @@ namespace
 {
 constexpr int LEAF = 128;
 constexpr int LP = 132;			 // pitch (doubles): 4 (mod 16) -> conflict-free DMMA fragment loads
-constexpr int LEAF_THREADS = 256; // 8 warps
-constexpr int PW = 16;			 // panel width / inverse block size
-constexpr size_t LEAF_SMEM = (size_t(LEAF) * LP + 8 * 16 * 20) * sizeof(double);
+constexpr int LEAF_THREADS = 256; // 8 warps: 0-3 factorise, 4-7 build the inverse underneath
+constexpr int FW = 8;			 // panel width = DMMA tile = granularity of the inverse
+constexpr int SPW = 32;			 // super-panel: trailing matrix updated once per 32 columns (rank-32 DMMA update)
+constexpr int TWS = 8 * 10;		 // per-warp 8 x 8 transposition scratch, pitch 10
+// S[128][LP] | Ld[16][8][8] factorised diagonal blocks | rsd[128] reciprocal pivots | tws[8 warps][4 tiles][TWS]
+constexpr size_t LEAF_SMEM = (size_t(LEAF) * LP + (LEAF / FW) * FW * FW + LEAF + 8 * 4 * TWS) * sizeof(double);
 
-/// 1 / sqrt(d) for the pivots: single-precision MUFU seed + two Newton steps in FP64 (error ~1 ulp), a much shorter
-/// dependent chain than the library rsqrt(double); outside the float range it falls back to the library.
+/// 1 / sqrt(d) for the pivots: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~22 bits) + two Newton steps in FP64 (error ~1 ulp):
+/// 90 cycles of dependent latency against ~125 for the float seed with its two conversions and far more for the library
+/// rsqrt(double) (profiles/r02_leaf_latency.md); outside the normal range it falls back to the library.
 __device__ __forceinline__ double fast_rsqrt(const double d)
 {
-	if (!(d > 1e-30 && d < 1e30))
+	if (!(d > 1e-290 && d < 1e290))
 	{
 		return rsqrt(d);
 	}
-	double y = double(rsqrtf(float(d)));
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
 	const double h = 0.5 * d;
 	y = y * fma(-h * y, y, 1.5);
 	y = y * fma(-h * y, y, 1.5);
 	return y;
 }
 
-/// Factor one 128 x 128 diagonal block and invert the resulting triangle, entirely in shared memory.
-///   factor : right-looking with 8-wide panels -- the 8 x 8 diagonal block factorised redundantly in the registers of
-///            every thread that owns a panel row (no shuffles, no barrier between block and panel), one row-wise
-///            triangular solve per thread, and the rank-8 trailing update of the lower triangle by all warps on DMMA;
-///   inverse: X = L^-1 by 16 x 16 blocks -- diagonal blocks by forward substitution (16 lanes each), then block
-///            sub-diagonal after sub-diagonal  X_ij = -X_ii sum_{k=j}^{i-1} L_ik X_kj  on DMMA, one warp per block.
-/// L lives in the lower triangle of S (row-major, pitch LP); X is kept TRANSPOSED in the strictly-upper part,
-/// shifted by one column: X[a][b] (a >= b) = S[b][a + 1].
+__device__ __forceinline__ void named_barrier(const int id, const int count)
+{
+	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+/// X_ii = L_ii^-1 of one 8 x 8 diagonal block by forward substitution, lane b (< 8) owning column b; the reciprocal pivots
+/// come from the factorisation.  Stored with the rest of X: X[a][b] (a >= b) = S[b][a + 1].
+__device__ __forceinline__ void inverse_diagonal_block(double* __restrict__ S, const double* __restrict__ Lb, const double* __restrict__ rs, const int i, const int b)
+{
+	double x[FW];
+#pragma unroll
+	for (int a = 0; a < FW; a++)
+	{
+		double v = 0.0;
+#pragma unroll
+		for (int k = 0; k < a; k++)
+		{
+			v = fma(-Lb[a * FW + k], x[k], v); // x[k] == 0 for k < b
+		}
+		x[a] = a == b ? rs[a] : (a > b ? v * rs[a] : 0.0);
+	}
+#pragma unroll
+	for (int a = 0; a < FW; a++)
+	{
+		if (a >= b)
+		{
+			S[(i * FW + b) * LP + i * FW + a + 1] = x[a];
+		}
+	}
+}
+
+/// Rows 8 i .. 8 i + 7 of X = L^-1 below the diagonal block (which inverse_diagonal_block has stored already):
+///     X_ij = -X_ii sum_{k = j}^{i - 1} L_ik X_kj   (j < i)
+/// on DMMA.  Warp w of nw takes the column tiles j = w, w + nw, ... (at most four), all in flight together: the L_ik
+/// fragment of a k-step is loaded once and feeds every tile that has reached k; the two k-halves of a step accumulate
+/// separately, so a warp runs up to eight independent DMMA chains and the tensor pipe, not the chain latency, is the limit.
+/// L lives in the lower triangle of S; X is kept TRANSPOSED in the strictly-upper part, shifted by one column.
+__device__ __forceinline__ void inverse_row_block(double* __restrict__ S, double* __restrict__ ws, const int i, const int w, const int nw, const int lane)
+{
+	const int g = lane >> 2, t = lane & 3;
+	constexpr int MAXT = 4;
+	if (w >= i)
+	{
+		return;
+	}
+	double acc[MAXT][2][2];
+#pragma unroll
+	for (int u = 0; u < MAXT; u++)
+	{
+		acc[u][0][0] = acc[u][0][1] = acc[u][1][0] = acc[u][1][1] = 0.0;
+	}
+	const double* __restrict__ Lrow = S + (i * FW + g) * LP + t; // L_ik[g][kk * 4 + t] at Lrow[k * 8 + kk * 4]
+	for (int k = w; k < i; k++)
+	{
+		const double a0 = Lrow[k * FW], a1 = Lrow[k * FW + 4];
+#pragma unroll
+		for (int u = 0; u < MAXT; u++)
+		{
+			const int j = w + u * nw;
+			if (j <= k) // warp-uniform; j < i follows from k < i
+			{
+				const double* __restrict__ Xc = S + (j * FW + g) * LP + k * FW + t + 1; // X_kj[kk * 4 + t][g]
+				double b0 = Xc[0], b1 = Xc[4];
+				if (k == j)
+				{
+					// X_jj is lower triangular (the slots above hold entries of L)
+					b0 = t < g ? 0.0 : b0;
+					b1 = t + 4 < g ? 0.0 : b1;
+				}
+				gemm::dmma884(acc[u][0], a0, b0);
+				gemm::dmma884(acc[u][1], a1, b1);
+			}
+		}
+	}
+	// T_j (accumulator layout C[g][2t .. 2t + 1]) -> scratch, re-read as the B operand T[tp][g] of  R = X_ii T_j
+	__syncwarp();
+#pragma unroll
+	for (int u = 0; u < MAXT; u++)
+	{
+		if (w + u * nw < i)
+		{
+			ws[u * TWS + g * 10 + 2 * t] = acc[u][0][0] + acc[u][1][0];
+			ws[u * TWS + g * 10 + 2 * t + 1] = acc[u][0][1] + acc[u][1][1];
+		}
+	}
+	__syncwarp();
+	const double xa0 = g >= t ? S[(i * FW + t) * LP + i * FW + g + 1] : 0.0;		 // X_ii[g][t]
+	const double xa1 = g >= t + 4 ? S[(i * FW + t + 4) * LP + i * FW + g + 1] : 0.0; // X_ii[g][t + 4]
+#pragma unroll
+	for (int u = 0; u < MAXT; u++)
+	{
+		const int j = w + u * nw;
+		if (j < i)
+		{
+			double r[2] = {0.0, 0.0};
+			gemm::dmma884(r, xa0, ws[u * TWS + t * 10 + g]);
+			gemm::dmma884(r, xa1, ws[u * TWS + (t + 4) * 10 + g]);
+			// X_ij[g][2t + u'] -> S[8 j + 2t + u'][8 i + g + 1]
+			S[(j * FW + 2 * t) * LP + i * FW + g + 1] = -r[0];
+			S[(j * FW + 2 * t + 1) * LP + i * FW + g + 1] = -r[1];
+		}
+	}
+}
+
+/// Factor one 128 x 128 diagonal block and invert the resulting triangle, entirely in shared memory, in one CTA.
+///   factor : right-looking over 8-wide panels inside 32-wide super-panels.  Per panel, phase 1: the 8 x 8 diagonal block is
+///            factorised REDUNDANTLY in the registers of every thread that owns a row below it (no shuffles, no barrier between
+///            block and row solve: the serial chain per column is rsqrt -> scale -> fma), then the thread solves its own row;
+///            phase 2: all warps apply the rank-8 update on DMMA, but only to the rest of the 32-wide super-panel; the trailing
+///            matrix beyond it gets ONE rank-32 update per super-panel (16 x 16 warp tiles, 8 k-steps: tensor-pipe bound
+///            instead of the latency-bound rank-8 sweeps over the whole trailing triangle).
+///   inverse: hidden underneath.  Phase 1 keeps at most 120 threads busy, so warps 4-7 build rows 8 (p - 1) .. of X = L^-1
+///            (inverse_row_block) while warps 0-3 factorise panel p; only the last row block is left for after the loop.
+/// The factorised diagonal blocks are parked in Ld (nobody reads them from S during the sweep) and copied back at the end,
+/// so that no thread can overwrite a diagonal block another thread is still loading.
 /// L overwrites the block (upper part zeroed); its inverse goes to `dinv` (row-major 128 x 128, upper part zero).
-__global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __restrict__ A, const size_t ld, double* __restrict__ dinv, int* __restrict__ info, const int global_row0)
+template <bool TIMED>
+__global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __restrict__ A, const size_t ld, double* __restrict__ dinv, int* __restrict__ info, const int global_row0, long long* __restrict__ ticks)
 {
 	extern __shared__ __align__(16) double sm[];
-	double* S = sm;					 // [128][LP]
-	double* scratch = sm + LEAF * LP; // [8 warps][16][20]
+	double* S = sm;						   // [128][LP]
+	double* Ld = sm + LEAF * LP;		   // [16][8][8]
+	double* rsd = Ld + (LEAF / FW) * FW * FW; // [128]
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+	double* ws = rsd + LEAF + warp * 4 * TWS;
+	// TIMED (profiles/tools/microbench_fp64.cu only): clock64 at the phase boundaries, as seen by thread 0
+	long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	auto stamp = [&](const int i)
+	{
+		if (TIMED)
+		{
+			tk[i] = clock64();
+		}
+	};
+	stamp(0);
+	// lower triangle -> shared memory: every 16-byte chunk in flight at once (LDGSTS)
 	for (int e = tid; e < LEAF * LEAF / 2; e += LEAF_THREADS)
 	{
 		const int r = e >> 6, c2 = (e & 63) * 2;
 		if (c2 <= r)
 		{
-			*reinterpret_cast<double2*>(S + r * LP + c2) = *reinterpret_cast<const double2*>(A + size_t(r) * ld + c2);
+			gemm::cp_async16(S + r * LP + c2, A + size_t(r) * ld + c2);
 		}
 	}
+	gemm::cp_async_commit();
+	gemm::cp_async_wait<0>();
 	__syncthreads();
+	stamp(1);
 
-	// ---------------------------------------------------------------- factor
-	// Right-looking with 8-wide panels.  The 8 x 8 diagonal block is factorised REDUNDANTLY by every thread that needs it,
-	// entirely in registers (36 doubles, no shuffles, no barrier): the serial chain per column is rsqrt -> scale -> fma.
-	// The same thread then solves its own panel row against its register copy of L_d (8-step substitution, the pivots'
-	// reciprocals come for free from the factorisation), and all warps apply the rank-8 trailing update on DMMA.
-	// The factorised diagonal blocks are parked in `scratch` (nobody reads them during the sweep) and copied back at the end,
-	// so that no thread can overwrite a diagonal block another thread is still loading.
-	constexpr int FW = 8;
-	double* Ld = scratch; // [16 panels][8][8]
+	long long part[5] = {0, 0, 0, 0, 0}, c_start = TIMED ? clock64() : 0;
 	for (int p = 0; p < LEAF / FW; p++)
 	{
 		const int c0 = p * FW;
-		const int rows_below = LEAF - c0 - FW;
-		if (tid < rows_below || tid == LEAF_THREADS - 1)
+		const int rows_below = LEAF - c0 - FW; // <= 120: thread 127 never owns a row and keeps the block for everybody
+		// ------------------------------------------------------------ phase 1
+		if (warp < 4)
 		{
-			double l[FW][FW], rs[FW];
-#pragma unroll
-			for (int i = 0; i < FW; i++)
+			// threads 120 .. 127 never own a row (rows_below <= 120): they factorise the block as well and each of them
+			// inverts one column of it (X_pp), which the inverse warps need one panel later; 127 also parks the block in Ld
+			if (tid < rows_below || tid >= 120)
 			{
-#pragma unroll
-				for (int k = 0; k <= i; k++)
-				{
-					l[i][k] = S[(c0 + i) * LP + c0 + k];
-				}
-			}
-			bool bad = false;
-#pragma unroll
-			for (int j = 0; j < FW; j++)
-			{
-				double d = l[j][j];
-				if (!(d > 0.0))
-				{
-					if (!bad && tid == LEAF_THREADS - 1)
-					{
-						atomicCAS(info, 0, global_row0 + c0 + j + 1);
-					}
-					bad = true;
-					d = 1.0;
-				}
-				rs[j] = fast_rsqrt(d);
-				l[j][j] = d * rs[j];
-#pragma unroll
-				for (int i = j + 1; i < FW; i++)
-				{
-					l[i][j] *= rs[j];
-				}
-#pragma unroll
-				for (int k = j + 1; k < FW; k++)
-				{
-#pragma unroll
-					for (int i = k; i < FW; i++)
-					{
-						l[i][k] = fma(-l[i][j], l[k][j], l[i][k]);
-					}
-				}
-			}
-			if (tid == LEAF_THREADS - 1)
-			{
+				double l[FW][FW], rs[FW];
 #pragma unroll
 				for (int i = 0; i < FW; i++)
 				{
 #pragma unroll
 					for (int k = 0; k <= i; k++)
 					{
-						Ld[p * FW * FW + i * FW + k] = l[i][k];
+						l[i][k] = S[(c0 + i) * LP + c0 + k];
 					}
 				}
-			}
-			else
-			{
-				// panel row r: x L_d^T = a
-				const int r = c0 + FW + tid;
-				double x[FW];
-#pragma unroll
-				for (int k = 0; k < FW; k += 2)
-				{
-					const double2 v = *reinterpret_cast<const double2*>(S + r * LP + c0 + k);
-					x[k] = v.x;
-					x[k + 1] = v.y;
-				}
+				bool bad = false;
 #pragma unroll
 				for (int j = 0; j < FW; j++)
 				{
-					double v = x[j];
-#pragma unroll
-					for (int k = 0; k < j; k++)
+					double d = l[j][j];
+					if (!(d > 0.0))
 					{
-						v = fma(-x[k], l[j][k], v);
+						if (!bad && tid == 127)
+						{
+							atomicCAS(info, 0, global_row0 + c0 + j + 1);
+						}
+						bad = true;
+						d = 1.0;
 					}
-					x[j] = v * rs[j];
-				}
+					rs[j] = fast_rsqrt(d);
+					l[j][j] = d * rs[j];
 #pragma unroll
-				for (int k = 0; k < FW; k += 2)
+					for (int i = j + 1; i < FW; i++)
+					{
+						l[i][j] *= rs[j];
+					}
+#pragma unroll
+					for (int k = j + 1; k < FW; k++)
+					{
+#pragma unroll
+						for (int i = k; i < FW; i++)
+						{
+							l[i][k] = fma(-l[i][j], l[k][j], l[i][k]);
+						}
+					}
+				}
+				if (tid >= 120)
 				{
-					*reinterpret_cast<double2*>(S + r * LP + c0 + k) = make_double2(x[k], x[k + 1]);
+					if (tid == 127)
+					{
+#pragma unroll
+						for (int i = 0; i < FW; i++)
+						{
+#pragma unroll
+							for (int k = 0; k <= i; k++)
+							{
+								Ld[p * FW * FW + i * FW + k] = l[i][k];
+							}
+						}
+					}
+					inverse_diagonal_block(S, &l[0][0], rs, p, tid - 120);
+				}
+				else
+				{
+					// panel row r: x L_d^T = a
+					const int r = c0 + FW + tid;
+					double x[FW];
+#pragma unroll
+					for (int k = 0; k < FW; k += 2)
+					{
+						const double2 v = *reinterpret_cast<const double2*>(S + r * LP + c0 + k);
+						x[k] = v.x;
+						x[k + 1] = v.y;
+					}
+#pragma unroll
+					for (int j = 0; j < FW; j++)
+					{
+						double v = x[j];
+#pragma unroll
+						for (int k = 0; k < j; k++)
+						{
+							v = fma(-x[k], l[j][k], v);
+						}
+						x[j] = v * rs[j];
+					}
+#pragma unroll
+					for (int k = 0; k < FW; k += 2)
+					{
+						*reinterpret_cast<double2*>(S + r * LP + c0 + k) = make_double2(x[k], x[k + 1]);
+					}
 				}
 			}
 		}
-		__syncthreads();
-		// trailing update of the lower triangle: A22 -= P P^T (k = 8), 8 x 8 tiles dealt round-robin to the warps,
-		// two tiles in flight per warp (the load -> DMMA -> store chain of one tile is pure latency)
+		else if (p > 0)
 		{
-			const int t0 = c0 + FW;
-			const int m = (LEAF - t0) / 8;
-			const int ntiles = m * (m + 1) / 2;
-			constexpr int NW = LEAF_THREADS / 32;
-			// tile idx -> (ti, tj), tj <= ti, advanced incrementally
-			int ti = 0, tj = warp;
-			auto normalise = [&]()
+			inverse_row_block(S, ws, p - 1, warp - 4, 4, lane);
+		}
+		long long c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+		if (TIMED)
+		{
+			c1 = clock64();
+			part[0] += c1 - c_start; // thread 0's own phase-1 work
+			if (__syncthreads_count(1) < 0) // a barrier whose result is consumed: the clock below is read after it completed
 			{
+				c1 = 0;
+			}
+		}
+		else
+		{
+			__syncthreads();
+		}
+		if (TIMED)
+		{
+			c2 = clock64();
+			part[1] += c2 - c1; // waiting for the slowest thread of phase 1 (the inverse group)
+		}
+		// ------------------------------------------------------------ phase 2
+		const int q = p & 3, s0 = c0 - q * FW, t0 = c0 + FW;
+		{
+			// rank-8 update of the rest of the super-panel: rows >= t0, columns [t0, s0 + 32), lower tiles only.  A warp owns the
+			// tile rows `warp` and `warp + 8` (there are at most 15); the up to three 8 x 8 tiles of a row share the A fragment,
+			// and all (up to six) load -> 2 DMMA -> store chains of the warp are in flight together
+			const int m = (LEAF - t0) / FW, nc = min(3 - q, m);
+			if (nc > 0 && warp < m)
+			{
+				int r0[2], cnt[2];
+				double a[2][2];
+				double2 cv[2][3];
+#pragma unroll
+				for (int h = 0; h < 2; h++)
+				{
+					const int ti = warp + 8 * h;
+					cnt[h] = ti < m ? min(ti + 1, nc) : 0;
+					r0[h] = t0 + (ti < m ? ti : warp) * FW;
+#pragma unroll
+					for (int kk = 0; kk < 2; kk++)
+					{
+						a[h][kk] = -S[(r0[h] + g) * LP + c0 + kk * 4 + t];
+					}
+#pragma unroll
+					for (int tj = 0; tj < 3; tj++)
+					{
+						cv[h][tj] = tj < cnt[h] ? *reinterpret_cast<const double2*>(S + (r0[h] + g) * LP + t0 + tj * FW + 2 * t) : make_double2(0.0, 0.0);
+					}
+				}
+				double b[3][2];
+#pragma unroll
+				for (int tj = 0; tj < 3; tj++)
+				{
+#pragma unroll
+					for (int kk = 0; kk < 2; kk++)
+					{
+						b[tj][kk] = tj < nc ? S[(t0 + tj * FW + g) * LP + c0 + kk * 4 + t] : 0.0;
+					}
+				}
+#pragma unroll
+				for (int kk = 0; kk < 2; kk++)
+				{
+#pragma unroll
+					for (int h = 0; h < 2; h++)
+					{
+#pragma unroll
+						for (int tj = 0; tj < 3; tj++)
+						{
+							if (tj < cnt[h])
+							{
+								double c[2] = {cv[h][tj].x, cv[h][tj].y};
+								gemm::dmma884(c, a[h][kk], b[tj][kk]);
+								cv[h][tj] = make_double2(c[0], c[1]);
+							}
+						}
+					}
+				}
+#pragma unroll
+				for (int h = 0; h < 2; h++)
+				{
+#pragma unroll
+					for (int tj = 0; tj < 3; tj++)
+					{
+						if (tj < cnt[h])
+						{
+							*reinterpret_cast<double2*>(S + (r0[h] + g) * LP + t0 + tj * FW + 2 * t) = cv[h][tj];
+						}
+					}
+				}
+			}
+		}
+		if (TIMED)
+		{
+			c3 = clock64();
+			part[2] += c3 - c2; // rank-8 update inside the super-panel
+		}
+		if (q == 3 && s0 + SPW < LEAF)
+		{
+			// the super-panel is complete: rank-32 update of everything beyond it, 16 x 16 warp tiles of the lower triangle
+			__syncthreads();
+			const int u0 = s0 + SPW, m2 = (LEAF - u0) / 16, ntiles = m2 * (m2 + 1) / 2;
+			for (int idx = warp; idx < ntiles; idx += 8)
+			{
+				int ti = 0, tj = idx;
 				while (tj > ti)
 				{
 					tj -= ti + 1;
 					ti++;
 				}
-			};
-			normalise();
-			for (int idx = warp; idx < ntiles; idx += 2 * NW)
-			{
-				const int r0 = t0 + ti * 8, q0 = t0 + tj * 8;
-				tj += NW;
-				normalise();
-				const bool second = idx + NW < ntiles;
-				const int r1 = second ? t0 + ti * 8 : r0, q1 = second ? t0 + tj * 8 : q0;
-				tj += NW;
-				normalise();
-				double2* cp0 = reinterpret_cast<double2*>(S + (r0 + g) * LP + q0 + 2 * t);
-				double2* cp1 = reinterpret_cast<double2*>(S + (r1 + g) * LP + q1 + 2 * t);
-				const double2 cv0 = *cp0, cv1 = *cp1;
-				double c0v[2] = {-cv0.x, -cv0.y}, c1v[2] = {-cv1.x, -cv1.y}; // accumulate -(A22) + P P^T, negate back on store
+				const int r0 = u0 + 16 * ti, q0 = u0 + 16 * tj;
+				const bool diag = ti == tj;
+				double acc[2][2][2];
 #pragma unroll
-				for (int kk = 0; kk < FW / 4; kk++)
+				for (int mi = 0; mi < 2; mi++)
 				{
-					const double a0 = S[(r0 + g) * LP + c0 + kk * 4 + t], b0 = S[(q0 + g) * LP + c0 + kk * 4 + t];
-					const double a1 = S[(r1 + g) * LP + c0 + kk * 4 + t], b1 = S[(q1 + g) * LP + c0 + kk * 4 + t];
-					gemm::dmma884(c0v, a0, b0);
-					gemm::dmma884(c1v, a1, b1);
+#pragma unroll
+					for (int nj = 0; nj < 2; nj++)
+					{
+						const double2 v = *reinterpret_cast<const double2*>(S + (r0 + 8 * mi + g) * LP + q0 + 8 * nj + 2 * t);
+						acc[mi][nj][0] = v.x;
+						acc[mi][nj][1] = v.y;
+					}
 				}
-				*cp0 = make_double2(-c0v[0], -c0v[1]);
-				if (second)
+#pragma unroll
+				for (int kk = 0; kk < SPW / 4; kk++)
 				{
-					*cp1 = make_double2(-c1v[0], -c1v[1]);
+					double a[2], b[2];
+#pragma unroll
+					for (int mi = 0; mi < 2; mi++)
+					{
+						a[mi] = -S[(r0 + 8 * mi + g) * LP + s0 + kk * 4 + t];
+						b[mi] = S[(q0 + 8 * mi + g) * LP + s0 + kk * 4 + t];
+					}
+					gemm::dmma884(acc[0][0], a[0], b[0]);
+					gemm::dmma884(acc[1][0], a[1], b[0]);
+					gemm::dmma884(acc[1][1], a[1], b[1]);
+					if (!diag)
+					{
+						gemm::dmma884(acc[0][1], a[0], b[1]);
+					}
+				}
+#pragma unroll
+				for (int mi = 0; mi < 2; mi++)
+				{
+#pragma unroll
+					for (int nj = 0; nj < 2; nj++)
+					{
+						if (!(diag && mi == 0 && nj == 1))
+						{
+							*reinterpret_cast<double2*>(S + (r0 + 8 * mi + g) * LP + q0 + 8 * nj + 2 * t) = make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+						}
+					}
 				}
 			}
 		}
-		__syncthreads();
+		if (TIMED)
+		{
+			c4 = clock64();
+			part[3] += c4 - c3; // rank-32 update
+		}
+		if (TIMED)
+		{
+			if (__syncthreads_count(1) < 0)
+			{
+				c4 = 0;
+			}
+			c_start = clock64();
+			part[4] += c_start - c4; // barrier at the end of the panel
+		}
+		else
+		{
+			__syncthreads();
+		}
 	}
+	stamp(2);
+	// last row block of the inverse, all warps
+	inverse_row_block(S, ws, LEAF / FW - 1, warp, 8, lane);
 	// factorised diagonal blocks back into place
 	for (int e = tid; e < (LEAF / FW) * FW * FW; e += LEAF_THREADS)
 	{
@@ -219,141 +481,42 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
 		}
 	}
 	__syncthreads();
-
-	// ---------------------------------------------------------------- inverse
-	// diagonal 16 x 16 blocks: block i by lanes 0..15 of warp i; lane b owns column b of X_ii
-	if (lane < PW)
+	stamp(3);
+	stamp(4);
+	// L (upper part zero) and X = L^-1 (transposed + shifted in S) out, 16 bytes per store
+	for (int e = tid; e < LEAF * LEAF / 2; e += LEAF_THREADS)
 	{
-		const int i0 = warp * PW, bcol = lane;
-		double x[PW];
-#pragma unroll
-		for (int a = 0; a < PW; a++)
-		{
-			double v = (a == bcol) ? 1.0 : 0.0;
-#pragma unroll
-			for (int k = 0; k < a; k++)
-			{
-				v = fma(-S[(i0 + a) * LP + i0 + k], (k >= bcol) ? x[k] : 0.0, v);
-			}
-			x[a] = (a >= bcol) ? v / S[(i0 + a) * LP + i0 + a] : 0.0;
-		}
-#pragma unroll
-		for (int a = 0; a < PW; a++)
-		{
-			if (a >= bcol)
-			{
-				S[(i0 + bcol) * LP + i0 + a + 1] = x[a]; // X[i0 + a][i0 + bcol], transposed + shifted
-			}
-		}
-	}
-	__syncthreads();
-	// block sub-diagonals d = 1 .. 7: block (i, j) = (j + d, j) by warp j
-	double* ws = scratch + warp * 16 * 20;
-	for (int d = 1; d < LEAF / PW; d++)
-	{
-		const int j = warp, i = j + d;
-		if (i < LEAF / PW)
-		{
-			// T = sum_{k = j}^{i - 1} L_ik X_kj   (16 x 16, as 2 x 2 DMMA tiles)
-			double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-			for (int k = j; k < i; k++)
-			{
-#pragma unroll
-				for (int kk = 0; kk < 4; kk++)
-				{
-					double av[2], bv[2];
-#pragma unroll
-					for (int mi = 0; mi < 2; mi++)
-					{
-						av[mi] = S[(i * PW + mi * 8 + g) * LP + k * PW + kk * 4 + t]; // L_ik[mi*8+g][kk*4+t]
-					}
-#pragma unroll
-					for (int nj = 0; nj < 2; nj++)
-					{
-						// X_kj[a][b], a = kk*4+t, b = nj*8+g, stored at S[j*16 + b][k*16 + a + 1]; X_jj is lower triangular
-						const int a = kk * 4 + t, b = nj * 8 + g;
-						const double v = S[(j * PW + b) * LP + k * PW + a + 1];
-						bv[nj] = (k > j || a >= b) ? v : 0.0;
-					}
-#pragma unroll
-					for (int mi = 0; mi < 2; mi++)
-					{
-#pragma unroll
-						for (int nj = 0; nj < 2; nj++)
-						{
-							gemm::dmma884(acc[mi][nj], av[mi], bv[nj]);
-						}
-					}
-				}
-			}
-			// T -> scratch (row-major 16 x 20) so that it can be re-read as a B operand
-#pragma unroll
-			for (int mi = 0; mi < 2; mi++)
-			{
-#pragma unroll
-				for (int nj = 0; nj < 2; nj++)
-				{
-					*reinterpret_cast<double2*>(ws + (mi * 8 + g) * 20 + nj * 8 + 2 * t) = make_double2(acc[mi][nj][0], acc[mi][nj][1]);
-				}
-			}
-			__syncwarp();
-			// R = X_ii T ; X_ij = -R
-			double r[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-#pragma unroll
-			for (int kk = 0; kk < 4; kk++)
-			{
-				double av[2], bv[2];
-#pragma unroll
-				for (int mi = 0; mi < 2; mi++)
-				{
-					// X_ii[a][b], a = mi*8+g, b = kk*4+t, stored at S[i*16 + b][i*16 + a + 1]; lower triangular
-					const int a = mi * 8 + g, b = kk * 4 + t;
-					const double v = S[(i * PW + b) * LP + i * PW + a + 1];
-					av[mi] = (a >= b) ? v : 0.0;
-				}
-#pragma unroll
-				for (int nj = 0; nj < 2; nj++)
-				{
-					bv[nj] = ws[(kk * 4 + t) * 20 + nj * 8 + g]; // T[kk*4+t][nj*8+g]
-				}
-#pragma unroll
-				for (int mi = 0; mi < 2; mi++)
-				{
-#pragma unroll
-					for (int nj = 0; nj < 2; nj++)
-					{
-						gemm::dmma884(r[mi][nj], av[mi], bv[nj]);
-					}
-				}
-			}
-			// X_ij[a][b] -> S[j*16 + b][i*16 + a + 1]
-#pragma unroll
-			for (int mi = 0; mi < 2; mi++)
-			{
-#pragma unroll
-				for (int nj = 0; nj < 2; nj++)
-				{
-#pragma unroll
-					for (int u = 0; u < 2; u++)
-					{
-						S[(j * PW + nj * 8 + 2 * t + u) * LP + i * PW + mi * 8 + g + 1] = -r[mi][nj][u];
-					}
-				}
-			}
-		}
-		__syncthreads();
-	}
-	for (int e = tid; e < LEAF * LEAF; e += LEAF_THREADS)
-	{
-		const int r = e >> 7, c = e & 127;
-		double l = 0.0, x = 0.0;
+		const int r = e >> 6, c = (e & 63) * 2;
+		double2 l = make_double2(0.0, 0.0), x = make_double2(0.0, 0.0);
 		if (c <= r)
 		{
-			l = S[r * LP + c];
-			x = S[c * LP + r + 1];
+			l.x = S[r * LP + c];
+			x.x = S[c * LP + r + 1];
 		}
-		A[size_t(r) * ld + c] = l;
-		dinv[e] = x;
+		if (c + 1 <= r)
+		{
+			l.y = S[r * LP + c + 1];
+			x.y = S[(c + 1) * LP + r + 1];
+		}
+		*reinterpret_cast<double2*>(A + size_t(r) * ld + c) = l;
+		*reinterpret_cast<double2*>(dinv + r * LEAF + c) = x;
+	}
+	if (TIMED)
+	{
+		stamp(5);
+		if (tid == 0)
+		{
+			// load, panel loop, last inverse row block + copy-back, store, total; then the loop split into its five parts
+			ticks[0] = tk[1] - tk[0];
+			ticks[1] = tk[2] - tk[1];
+			ticks[2] = tk[3] - tk[2];
+			ticks[3] = tk[5] - tk[4];
+			ticks[4] = tk[5] - tk[0];
+			for (int i = 0; i < 5; i++)
+			{
+				ticks[5 + i] = part[i];
+			}
+		}
 	}
 }
 
@@ -485,7 +648,7 @@ struct Chol
 
 	void leaf(const int o) const
 	{
-		GPLE_LAUNCH(ctx, potrf_leaf_kernel, 1, LEAF_THREADS, LEAF_SMEM, at(o, o), ld, dinv + size_t(o / LEAF) * LEAF * LEAF, info, o);
+		GPLE_LAUNCH(ctx, potrf_leaf_kernel<false>, 1, LEAF_THREADS, LEAF_SMEM, at(o, o), ld, dinv + size_t(o / LEAF) * LEAF * LEAF, info, o, static_cast<long long*>(nullptr));
 	}
 
 	/// rank-128 update C -= P P^T of the lower 128-tiles of a trailing block (C: m x nc at (r, c); P: the panel rows r.. and c..)
@@ -659,7 +822,7 @@ void chol_setup_attributes()
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::SmallConfig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SmallConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::SmallConfig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::SmallConfig::SMEM_BYTES)));
 	GPLE_CUDA(cudaFuncSetAttribute(gemm::gemm_kernel<gemm::StripConfig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm::StripConfig::SMEM_BYTES)));
-	GPLE_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LEAF_SMEM)));
+	GPLE_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LEAF_SMEM)));
 }
 
 void gemm_nt(gple_ctx* ctx, const gemm::GemmArgs& a)

@@ -159,6 +159,83 @@ void allreduce_sum(gple_ctx* ctx, double* d_values, const size_t count)
 	check_nccl(nccl().AllReduce(d_values, d_values, count, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->comm), ctx->stream), "ncclAllReduce");
 }
 
+/// One element model, trained on `root`, replicated on every rank: the owner sends a small header (sizes, parameters,
+/// scalars) and then its device buffers (X, W = L^-1, v, labels, diag(K^-1)); the other ranks allocate the same buffers from
+/// their own pools.  On entry *model is the trained model on the root and ignored elsewhere (NULL on every rank = the element
+/// is not populated: nothing is sent).  Kinv / dv (on-demand, derivative-only) are not replicated.
+void model_bcast(gple_ctx* ctx, gple_model** model, const int root)
+{
+	if (ctx->comm_size <= 1)
+	{
+		return;
+	}
+	const NcclApi& n = nccl();
+	const ncclComm_t c = static_cast<ncclComm_t>(ctx->comm);
+	struct Header
+	{
+		double present, is_complex, N, Np, n, flags, rescale, prior, theta[8];
+	};
+	static_assert(sizeof(Header) == 16 * sizeof(double), "header is 16 doubles");
+	Header h{};
+	const bool mine = ctx->comm_rank == root;
+	if (mine && *model != nullptr)
+	{
+		const gple_model* m = *model;
+		h.present = 1.0;
+		h.is_complex = m->is_complex;
+		h.N = double(m->N);
+		h.Np = m->Np;
+		h.n = m->n;
+		h.flags = m->flags;
+		h.rescale = m->rescale;
+		h.prior = m->prior;
+		std::memcpy(h.theta, m->theta, sizeof(h.theta));
+	}
+	double* d_h = ctx->ws.get<double>("comm.header", 16);
+	if (mine)
+	{
+		GPLE_CUDA(cudaMemcpyAsync(d_h, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+	}
+	check_nccl(n.Broadcast(d_h, d_h, 16, ncclDouble, root, c, ctx->stream), "ncclBroadcast(header)");
+	GPLE_CUDA(cudaMemcpyAsync(&h, d_h, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+	GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (h.present == 0.0)
+	{
+		if (!mine)
+		{
+			*model = nullptr;
+		}
+		return;
+	}
+	gple_model* m = mine ? *model : new gple_model();
+	const size_t nn = size_t(h.n), Np = size_t(h.Np);
+	if (!mine)
+	{
+		m->owner = ctx;
+		m->is_complex = int(h.is_complex);
+		m->N = size_t(h.N);
+		m->Np = int(h.Np);
+		m->n = int(h.n);
+		m->flags = unsigned(h.flags);
+		m->rescale = h.rescale;
+		m->prior = h.prior;
+		std::memcpy(m->theta, h.theta, sizeof(h.theta));
+		m->X = static_cast<double*>(ctx->pool.alloc(2 * Np * sizeof(double)));
+		m->W = static_cast<double*>(ctx->pool.alloc(nn * nn * sizeof(double)));
+		m->v = static_cast<double*>(ctx->pool.alloc(nn * sizeof(double)));
+		m->label = static_cast<double*>(ctx->pool.alloc(nn * sizeof(double)));
+		m->kinv_diag = static_cast<double*>(ctx->pool.alloc(3 * nn * sizeof(double)));
+	}
+	check_nccl(n.GroupStart(), "ncclGroupStart");
+	check_nccl(n.Broadcast(m->X, m->X, 2 * Np, ncclDouble, root, c, ctx->stream), "ncclBroadcast(X)");
+	check_nccl(n.Broadcast(m->W, m->W, nn * nn, ncclDouble, root, c, ctx->stream), "ncclBroadcast(W)");
+	check_nccl(n.Broadcast(m->v, m->v, nn, ncclDouble, root, c, ctx->stream), "ncclBroadcast(v)");
+	check_nccl(n.Broadcast(m->label, m->label, nn, ncclDouble, root, c, ctx->stream), "ncclBroadcast(label)");
+	check_nccl(n.Broadcast(m->kinv_diag, m->kinv_diag, 3 * nn, ncclDouble, root, c, ctx->stream), "ncclBroadcast(kinv_diag)");
+	check_nccl(n.GroupEnd(), "ncclGroupEnd");
+	*model = m;
+}
+
 /// evolve() over point sets that are block-partitioned over the ranks: every rank moves its own block of each element,
 /// then the blocks are all-gathered in place, so that every rank leaves with the full evolved sets.
 void evolve_sharded_device(gple_ctx* ctx, int pes_model, const gple_model* const models[3], double* d_pts[3], const size_t totals[3], double mass, double dt)

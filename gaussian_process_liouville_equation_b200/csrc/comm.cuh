@@ -22,5 +22,6 @@ void comm_init(gple_ctx* ctx, int rank, int nranks, const unsigned char* id);
 void comm_destroy(gple_ctx* ctx);
 void allgather_blocks(gple_ctx* ctx, double* d_all, size_t total, size_t width);
 void allreduce_sum(gple_ctx* ctx, double* d_values, size_t count);
+void model_bcast(gple_ctx* ctx, gple_model** model, int root);
 void evolve_sharded_device(gple_ctx* ctx, int pes_model, const gple_model* const models[3], double* d_pts[3], const size_t totals[3], double mass, double dt);
 } // namespace gple

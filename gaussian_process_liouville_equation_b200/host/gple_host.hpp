@@ -194,6 +194,23 @@ struct ContextSlot
 	ContextSlot& operator=(const ContextSlot&) = delete;
 };
 
+/// Multi-GPU: the element models are independent, so with G ranks element e is trained / optimised on ONE
+/// rank: the off-diagonal (complex, order 2N: the most expensive) element on rank 0, the diagonal ones on ranks 1 and 2
+/// (both on rank 1 when G = 2, everything on rank 0 when G = 1).
+inline int element_owner(const std::size_t element, const int num_ranks)
+{
+	const int owner[3] = {1 % num_ranks, 0, 2 % num_ranks};
+	return owner[element];
+}
+/// In-place sum over the ranks of a small host vector (every rank contributes zeros for what it does not own)
+inline void all_reduce_sum(std::vector<double>& v)
+{
+	if (Context::num_ranks() > 1 && !v.empty())
+	{
+		Context::check(gple_allreduce_sum(Context::main(), v.data(), v.size()), "all_reduce_sum");
+	}
+}
+
 /// Two persistent worker threads, bound to the context slots 1 and 2 (slot 0 is the calling thread).  An optimisation makes
 /// thousands of three-element evaluations of a millisecond or less each: spawning threads per evaluation would cost as much as
 /// the evaluation itself.
@@ -746,13 +763,17 @@ public:
 	using QuantumVectorD = std::array<double, NumPES>;
 
 	/// gple/predict.cpp:362-388; an element stays nullopt when its training set is empty or all its parameters are 0 (:339-357)
-	TrainingKernels(const std::array<ParameterVector, NumElements>& ParameterVectors, const AllTrainingSets& TrainingSets, bool IsToCalculateError, bool IsToCalculateAverage, bool IsToCalculateDerivative, ModelCache* Cache = nullptr)
+	/// Distributed (multi-GPU, optimiser callbacks only): every rank trains the elements it owns (element_owner) and the
+	/// averages and their derivatives are summed over the ranks, so the calculate_* / *_derivative getters return the same
+	/// numbers everywhere while each factorisation happens once; handle() / Diagonal / OffDiagonal are local-only then.
+	TrainingKernels(const std::array<ParameterVector, NumElements>& ParameterVectors, const AllTrainingSets& TrainingSets, bool IsToCalculateError, bool IsToCalculateAverage, bool IsToCalculateDerivative, ModelCache* Cache = nullptr, bool Distributed = false)
 	{
+		const int ranks = Distributed ? Context::num_ranks() : 1, me = ranks > 1 ? Context::rank() : 0;
 		for_each_element_concurrently(
 			[&](const std::size_t e)
 			{
 				const bool all_zero = std::all_of(ParameterVectors[e].cbegin(), ParameterVectors[e].cend(), [](double d) { return d == 0.0; });
-				if (std::get<0>(TrainingSets[e]).cols() == 0 || all_zero)
+				if (std::get<0>(TrainingSets[e]).cols() == 0 || all_zero || element_owner(e, ranks) != me)
 				{
 					return;
 				}
@@ -768,6 +789,40 @@ public:
 				}
 			}
 		);
+		// averages of the elements: [population, <x>, <p>, purity, d population (4), d purity (8)] per element
+		Averages.assign(NumElements * AvgStride, 0.0);
+		for (std::size_t i = 0; i < NumPES; i++)
+		{
+			if (Diagonal[i] && IsToCalculateAverage)
+			{
+				double* a = &Averages[2 * i * AvgStride];
+				a[0] = Diagonal[i]->get_population();
+				const ClassicalPhaseVector r = Diagonal[i]->get_1st_order_average();
+				a[1] = r[0];
+				a[2] = r[1];
+				a[3] = Diagonal[i]->get_purity();
+				if (IsToCalculateDerivative)
+				{
+					const auto dp = Diagonal[i]->get_population_derivative(), du = Diagonal[i]->get_purity_derivative();
+					std::copy(dp.cbegin(), dp.cend(), a + 4);
+					std::copy(du.cbegin(), du.cend(), a + 8);
+				}
+			}
+		}
+		if (OffDiagonal && IsToCalculateAverage)
+		{
+			double* a = &Averages[AvgStride];
+			a[3] = OffDiagonal->get_purity();
+			if (IsToCalculateDerivative)
+			{
+				const auto du = OffDiagonal->get_purity_derivative();
+				std::copy(du.cbegin(), du.cend(), a + 8);
+			}
+		}
+		if (ranks > 1)
+		{
+			all_reduce_sum(Averages);
+		}
 	}
 	/// gple/predict.cpp:390-393 (error = true, average = true, derivative = false)
 	TrainingKernels(const std::array<ParameterVector, NumElements>& ParameterVectors, const AllPoints& density):
@@ -776,42 +831,27 @@ public:
 	}
 	double calculate_population() const // gple/predict.cpp:395-406
 	{
-		double r = 0.0;
-		for (const auto& k : Diagonal)
-		{
-			r += k ? k->get_population() : 0.0;
-		}
-		return r;
+		return avg(0)[0] + avg(2)[0];
 	}
 	ClassicalPhaseVector calculate_1st_order_average() const // gple/predict.cpp:408-419
 	{
-		ClassicalPhaseVector r{0.0, 0.0};
-		for (const auto& k : Diagonal)
-		{
-			if (k)
-			{
-				const ClassicalPhaseVector a = k->get_1st_order_average();
-				r[0] += a[0];
-				r[1] += a[1];
-			}
-		}
-		return r;
+		return {avg(0)[1] + avg(2)[1], avg(0)[2] + avg(2)[2]};
 	}
 	double calculate_total_energy_average(const QuantumVectorD& Energies) const // gple/predict.cpp:423-436
 	{
 		double r = 0.0;
 		for (std::size_t i = 0; i < NumPES; i++)
 		{
-			r += Diagonal[i] ? Diagonal[i]->get_population() * Energies[i] : 0.0;
+			r += avg(2 * i)[0] * Energies[i];
 		}
 		return r;
 	}
 	double calculate_purity() const // gple/predict.cpp:439-463
 	{
-		double r = OffDiagonal ? 2.0 * OffDiagonal->get_purity() : 0.0;
-		for (const auto& k : Diagonal)
+		double r = 2.0 * avg(1)[3];
+		for (std::size_t i = 0; i < NumPES; i++)
 		{
-			r += k ? k->get_purity() : 0.0;
+			r += avg(2 * i)[3];
 		}
 		return r;
 	}
@@ -821,11 +861,7 @@ public:
 		ParameterVector r(4 * NumPES, 0.0);
 		for (std::size_t i = 0; i < NumPES; i++)
 		{
-			if (Diagonal[i])
-			{
-				const auto d = Diagonal[i]->get_population_derivative();
-				std::copy(d.cbegin(), d.cend(), r.begin() + 4 * i);
-			}
+			std::copy(avg(2 * i) + 4, avg(2 * i) + 8, r.begin() + 4 * i);
 		}
 		return r;
 	}
@@ -846,21 +882,9 @@ public:
 	ParameterVector purity_derivative() const
 	{
 		ParameterVector r(NumTotalParameters, 0.0);
-		if (Diagonal[0])
-		{
-			const auto d = Diagonal[0]->get_purity_derivative();
-			std::copy(d.cbegin(), d.cend(), r.begin());
-		}
-		if (OffDiagonal)
-		{
-			const auto d = OffDiagonal->get_purity_derivative();
-			std::transform(d.cbegin(), d.cend(), r.begin() + 4, [](double x) { return 2.0 * x; });
-		}
-		if (Diagonal[1])
-		{
-			const auto d = Diagonal[1]->get_purity_derivative();
-			std::copy(d.cbegin(), d.cend(), r.begin() + 12);
-		}
+		std::copy(avg(0) + 8, avg(0) + 12, r.begin());
+		std::transform(avg(1) + 8, avg(1) + 16, r.begin() + 4, [](double x) { return 2.0 * x; });
+		std::copy(avg(2) + 8, avg(2) + 12, r.begin() + 12);
 		return r;
 	}
 	const gple_model* handle(std::size_t element) const
@@ -874,6 +898,11 @@ public:
 	/// empty = the reference's std::nullopt (element not populated); shared so that a ModelCache can serve the same model twice
 	std::array<std::shared_ptr<const TrainingKernel>, NumPES> Diagonal;
 	std::shared_ptr<const TrainingComplexKernel> OffDiagonal;
+
+private:
+	static constexpr std::size_t AvgStride = 16;
+	std::vector<double> Averages; // NumElements x AvgStride, zeros for an absent element
+	const double* avg(const std::size_t element) const { return &Averages[element * AvgStride]; }
 };
 
 /// gple/evolve.h:16-21 with the GPR-backed predict_distribution of gple/main.cpp:75-101

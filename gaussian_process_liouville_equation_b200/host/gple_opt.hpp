@@ -148,10 +148,12 @@ inline double sum_loose(const ParameterVector& x, ParameterVector& grad, const A
 {
 	std::array<double, NumElements> value{0.0, 0.0, 0.0};
 	std::array<ParameterVector, NumElements> g;
+	// multi-GPU: every element's loss on the rank that owns the element, values and gradients summed over the ranks
+	const int ranks = Context::num_ranks(), me = ranks > 1 ? Context::rank() : 0;
 	for_each_element_concurrently(
 		[&](const std::size_t e)
 		{
-			if (!use[e] || std::get<0>(ts[e]).cols() == 0)
+			if (!use[e] || std::get<0>(ts[e]).cols() == 0 || element_owner(e, ranks) != me)
 			{
 				return;
 			}
@@ -162,6 +164,24 @@ inline double sum_loose(const ParameterVector& x, ParameterVector& grad, const A
 			value[e] = loose_function(xe, g[e], static_cast<void*>(&etp));
 		}
 	);
+	if (ranks > 1)
+	{
+		std::vector<double> buf(NumElements * 9, 0.0);
+		for (std::size_t e = 0; e < NumElements; e++)
+		{
+			buf[e * 9] = value[e];
+			std::copy(g[e].cbegin(), g[e].cend(), buf.begin() + e * 9 + 1);
+		}
+		all_reduce_sum(buf);
+		for (std::size_t e = 0; e < NumElements; e++)
+		{
+			value[e] = buf[e * 9];
+			if (use[e] && std::get<0>(ts[e]).cols() != 0)
+			{
+				g[e].assign(buf.cbegin() + e * 9 + 1, buf.cbegin() + e * 9 + 1 + (grad.empty() ? 0 : (e == 1 ? 8 : 4)));
+			}
+		}
+	}
 	double err = 0.0;
 	for (std::size_t e = 0; e < NumElements; e++)
 	{
@@ -200,7 +220,7 @@ inline void diagonal_constraints(const unsigned m, double* result, const unsigne
 	assert(n == 8 && (m == 2 || m == 3));
 	// construct_all_parameters_from_diagonal (opt.cpp:622-636): the off-diagonal element is absent (all-zero parameters)
 	const AllParameters all{ParameterVector(x, x + 4), ParameterVector(8, 0.0), ParameterVector(x + 4, x + 8)};
-	const TrainingKernels k(all, ts, true, true, grad != nullptr, &ModelCache::instance());
+	const TrainingKernels k(all, ts, true, true, grad != nullptr, &ModelCache::instance(), true);
 	result[0] = k.calculate_population() - 1.0;
 	result[1] = k.calculate_total_energy_average(Energies) - TotalEnergy;
 	if (m == 3)
@@ -234,7 +254,7 @@ inline void full_constraints(const unsigned m, double* result, const unsigned n,
 	const auto& [ts, Energies, TotalEnergy, Purity] = *static_cast<AnalyticalConstraintParameters*>(params);
 	assert(n == 16 && m == 3);
 	const AllParameters all{ParameterVector(x, x + 4), ParameterVector(x + 4, x + 12), ParameterVector(x + 12, x + 16)};
-	const TrainingKernels k(all, ts, true, true, grad != nullptr, &ModelCache::instance());
+	const TrainingKernels k(all, ts, true, true, grad != nullptr, &ModelCache::instance(), true);
 	result[0] = k.calculate_population() - 1.0;
 	result[1] = k.calculate_total_energy_average(Energies) - TotalEnergy;
 	result[2] = k.calculate_purity() - Purity;
@@ -561,10 +581,13 @@ private:
 	{
 		std::array<double, NumElements> err{0.0, 0.0, 0.0};
 		std::vector<std::size_t> steps(NumElements, 0);
+		// multi-GPU: an element's optimisation runs on the rank that owns the element; parameters, error and evaluation count
+		// are then summed over the ranks (zeros elsewhere), so every rank continues from identical parameters
+		const int ranks = Context::num_ranks(), me = ranks > 1 ? Context::rank() : 0;
 		for_each_element_concurrently(
 			[&](const std::size_t e)
 			{
-				if (std::get<0>(ts[e]).cols() == 0)
+				if (std::get<0>(ts[e]).cols() == 0 || element_owner(e, ranks) != me)
 				{
 					return;
 				}
@@ -585,6 +608,29 @@ private:
 				steps[e] = std::size_t(o.get_numevals());
 			}
 		);
+		if (ranks > 1)
+		{
+			std::vector<double> buf(NumElements * 10, 0.0);
+			for (std::size_t e = 0; e < NumElements; e++)
+			{
+				if (std::get<0>(ts[e]).cols() != 0 && element_owner(e, ranks) == me)
+				{
+					std::copy(pv[e].cbegin(), pv[e].cend(), buf.begin() + e * 10);
+					buf[e * 10 + 8] = err[e];
+					buf[e * 10 + 9] = double(steps[e]);
+				}
+			}
+			all_reduce_sum(buf);
+			for (std::size_t e = 0; e < NumElements; e++)
+			{
+				if (std::get<0>(ts[e]).cols() != 0)
+				{
+					std::copy(buf.cbegin() + e * 10, buf.cbegin() + e * 10 + pv[e].size(), pv[e].begin());
+					err[e] = buf[e * 10 + 8];
+					steps[e] = std::size_t(buf[e * 10 + 9]);
+				}
+			}
+		}
 		return {err[0] + err[1] + err[2], steps};
 	}
 	/// optimize_diagonal (gple/opt.cpp:730-800)

@@ -211,6 +211,13 @@ extern "C"
 	int gple_allgather_points(gple_ctx* ctx, double* pts, size_t total);
 	/* sum over the ranks of `count` doubles, in place (partial sums of gple_observables / gple_validation_error over sharded points) */
 	int gple_allreduce_sum(gple_ctx* ctx, double* values, size_t count);
+	/* Element models are independent (gple/predict.cpp:390-393 builds them in a parallel loop): on G GPUs each
+	 * model of the TrainingKernels rebuild is trained on ONE rank (a factorisation never spans GPUs) and replicated with this
+	 * call -- collective over the communicator.  On `root`, *model is the trained model (NULL: element not populated); on the
+	 * other ranks *model receives a copy that lives in this context's pool (or NULL), to be freed with gple_model_destroy.
+	 * Replicates what prediction and the scalar getters need (X, L^-1, K^-1 y', labels, diag K^-1); the on-demand full
+	 * inverse and the derivative arrays stay with the root. */
+	int gple_model_bcast(gple_ctx* ctx, gple_model** model, int root);
 	/* gple_evolve over point sets that are block-partitioned over the ranks: pts?? are the FULL sets (n?? = their full sizes);
 	 * every rank evolves its own block of each element and the blocks are all-gathered in place, so that every rank returns
 	 * with the full evolved sets -- evolve(density) of main.cpp:140 on G GPUs.  Identical to gple_evolve without a communicator. */

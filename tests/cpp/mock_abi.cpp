@@ -194,6 +194,7 @@ extern "C"
 		}
 		return GPLE_OK;
 	}
+	int gple_allreduce_sum(gple_ctx*, double*, size_t) { return GPLE_OK; }
 	int gple_evolve_sharded(gple_ctx* ctx, int pes_model, const gple_model* m00, const gple_model* m10, const gple_model* m11, double* pts00, size_t n00, double* pts10, size_t n10, double* pts11, size_t n11, double mass, double dt)
 	{
 		return gple_evolve(ctx, pes_model, m00, m10, m11, pts00, n00, pts10, n10, pts11, n11, mass, dt);
