@@ -21,6 +21,8 @@ def parse(out):
     ticks, info = [], {}
     for line in out.strip().splitlines():
         w = line.split()
+        if not w or w[0] == "NCCL":  # the NCCL banner ("NCCL version ...") goes to stdout on rank 0
+            continue
         if w[0] == "tick":
             ticks.append([float(v) for v in w[2:]])
         else:
