@@ -409,7 +409,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     ctx.profile_enable(True)
-    for slot in range(3):
+    for slot in range(4):
         ctx.profile_read(slot)
     for c in train_ctx[:2]:
         c.profile_enable(True)
@@ -417,7 +417,7 @@ def run_ours(args):
     launches0 = sum(c.launches for c in train_ctx)
     total_ms = timed(resident, args.steps)
     launches = sum(c.launches for c in train_ctx) - launches0
-    prof = [ctx.profile_read(slot) for slot in range(3)]
+    prof = [ctx.profile_read(slot) for slot in range(4)]
     for c in train_ctx[:2]:  # factorisations of the two real elements ran concurrently on their own streams
         ms, n_, w_ = c.profile_read(2)
         prof[2] = (prof[2][0] + ms, prof[2][1] + n_, prof[2][2] + w_)
@@ -449,6 +449,7 @@ def run_ours(args):
     var_ms, var_n, var_flops = prof[0]
     kb_ms, kb_n, kb_bytes = prof[1]
     fa_ms, fa_n, fa_flops = prof[2]
+    mean_ms, mean_n, mean_exps = prof[3]
     achieved = var_flops / (var_ms * 1e-3) / 1e12 if var_ms > 0 else 0.0
     # algorithmic flops of the reference formulation (2 Q N^2 per real query set, 16 Q N^2 complex)
     alg_flops_step = 8 * nloc * (2 + 2 + 16) * float(N_TRAIN) ** 2 + (1 + 1 + 24 + 1.0 / 3.0) * float(N_TRAIN) ** 3
@@ -470,6 +471,8 @@ def run_ours(args):
         "extra": {"fp64_dfma_peak_tflops": dfma_peak, "dmma_register_tile_ceiling_tflops": tile_peak,
                   "dmma_register_tile_ceiling_note": "same 8x4 DMMA register tile at 8 warps/SM with changing operands and no memory traffic: the ceiling of an mma.sync FP64 GEMM at this occupancy",
                   "kernel_build_gbs": kb_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else None, "kernel_build_share": kb_ms / total_ms,
+                  "mean_pass_share": mean_ms / total_ms, "mean_pass_gexp_per_s": mean_exps / (mean_ms * 1e-3) / 1e9 if mean_ms > 0 else None,
+                  "mean_pass_note": "kmean_kernel: K* v for all 8Q queries without storing K*; FP64-pipe bound (DFMA shares the pipe with DMMA, profiles/r02_kstar_fusion_decision.md): 19.5 FP64 instructions per kernel value with the table-based exp of csrc/gpr.cu",
                   "cholesky_inverse_tflops": fa_flops / (fa_ms * 1e-3) / 1e12 if fa_ms > 0 else None, "factorise_share": fa_ms / total_ms,
                   "gated_variance": {"enabled": True, "rows_total": rows_total, "rows_through_variance_gemm": rows_var, "rows_decided_zero": rows_zero, "rows_needing_the_full_variance": rows_b,
                                      "fraction": rows_var / max(rows_total, 1), "fraction_full": rows_b / max(rows_total, 1),

@@ -28,6 +28,76 @@ namespace
 // covariance construction
 // ---------------------------------------------------------------------------------------------------
 
+// exp(-s / 2), s >= 0, for the test-vs-training covariance rows (kmean_kernel / kstar_kernel): those two kernels evaluate
+// 8 Q N exponentials per element and step and are bound by the FP64 pipe, which DFMA shares with DMMA on B200
+// (profiles/r02_kstar_fusion_decision.md), so what counts is the number of FP64 instructions per kernel value -- and, right
+// behind it, the number of instructions of any kind (one issue slot per cycle and scheduler against two cycles per FP64
+// instruction).  The library exp() spends about 17 FP64 instructions (degree-11 polynomial); this one 11:
+//   k = rint(-s * 16 / ln 2),  exp(-s / 2) = 2^(k >> 5) * T[k & 31] * exp(r),  T[j] = 2^(j / 32) from shared memory (32 x 8 bytes:
+//   at most a two-way bank conflict),  |r| <= ln 2 / 64,  degree-6 Taylor polynomial (remainder 3.5e-18);
+// the power of two goes into the exponent field of the prefactor sigma_f^2 on the integer pipe, so that scaling and prefactor
+// are ONE multiplication.  Error <= 2 ulp.  The hot loop carries no special cases at all: it only tracks, per row, whether
+// some s was exactly zero (a query that coincides with a training point: the delta term of kernel.cpp:8-31) or outside
+// [2^-1022, 1270) (underflow of the result, Inf, NaN); such a row -- rare -- is recomputed as a whole with the library exp and the
+// exact coincidence predicate (gauss_value), in the same summation order.  Whether a row is recomputed depends on its data
+// only, never on which kernel evaluates it, so predictions stay bit-identical across kmean_kernel<*> and kstar_kernel.
+__constant__ double c_exp2_tab[32] = {
+	0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0, 0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+	0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0, 0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+	0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0, 0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+	0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0, 0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+
+/// every thread of the CTA calls this before the first fast_kernel_value; includes the barrier
+__device__ __forceinline__ void load_exp_table(double* __restrict__ tab)
+{
+	if (threadIdx.x < 32)
+	{
+		tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+	}
+	__syncthreads();
+}
+
+/// `track` trips (>= FAST_TRIP) when the high word of some s was 0 (s == 0 or denormal) or >= that of 1270.0 (large, Inf, NaN,
+/// negative): unsigned(hi) - 1 maps 0 to 0xFFFFFFFF
+constexpr unsigned FAST_TRIP = 0x4093D800u - 1u;
+
+/// a block's prefactor must leave room in the exponent field for 2^(k >> 5) >= 2^-917 and for the table value: 2^-100 .. 2^100
+__device__ __forceinline__ bool fast_prefactor_ok(const GaussBlock& g)
+{
+	const unsigned e = (unsigned(__double2hiint(g.mag2)) >> 20) & 0x7FFu; // sign bit dropped: mag2 may be negative (cross block)
+	return e >= 1023u - 100u && e <= 1023u + 100u;
+}
+
+/// sigma_f^2 exp(-r^2 / 2) without the coincidence term, valid when `track` does not trip for the row (else garbage)
+__device__ __forceinline__ double fast_kernel_value(const GaussBlock& g, const double2 a, const double2 c, const double* __restrict__ tab, unsigned& track)
+{
+	const double dx = (a.x - c.x) * g.inv_lx, dp = (a.y - c.y) * g.inv_lp;
+	const double s = fma(dp, dp, dx * dx);
+	track = max(track, unsigned(__double2hiint(s)) - 1u);
+	const double t = fma(s, -0x1.71547652b82fep+4, 6755399441055744.0); // -16 / ln 2; 1.5 * 2^52: the low word of t is k
+	const int k = __double2loint(t);
+	const double kf = t - 6755399441055744.0;
+	double r = fma(kf, 0x1.62e42fee00000p-5, s); // r = s + k * (2 ln 2 / 32) = -2 * (reduced argument); the product is exact
+	r = fma(kf, 0x1.a39ef35793c76p-37, r);
+	double p = fma(0x1.6c16c16c16c17p-16, r, -0x1.1111111111111p-12); // sum_n (-1/2)^n r^n / n!
+	p = fma(p, r, 0x1.5555555555555p-9);
+	p = fma(p, r, -0x1.5555555555555p-6);
+	p = fma(p, r, 0x1.0000000000000p-3);
+	p = fma(p, r, -0.5);
+	const double T = tab[k & 31];
+	const double v = fma(T, p * r, T);
+	// sigma_f^2 * 2^(k >> 5): (k >> 5) << 20 == (k << 15) & 0xFFF00000 added to the high word (k <= 0; no carry out of the field)
+	const double m = __hiloint2double(__double2hiint(g.mag2) + ((k << 15) & 0xFFF00000), __double2loint(g.mag2));
+	return v * m;
+}
+
+/// the exact evaluation (library exp, coincidence term of kernel.cpp:8-31) used for the rows the fast path flags
+__device__ __forceinline__ double exact_kernel_value(const GaussBlock& g, const double2 a, const double2 c, bool& same)
+{
+	same = a.x == c.x && a.y == c.y;
+	return gauss_value(g, a, c) + (same ? g.diag_add : 0.0);
+}
+
 /// Lower 128-tiles of the (composite) training covariance, row-major n x n with n = nb * Np.
 /// Padding rows/columns (point index >= N) carry the identity so the factorisation stays decoupled.
 __global__ void __launch_bounds__(256) build_cov_lower_kernel(const BlockSpec spec, const double2* __restrict__ X, const int N, const int Np, const int n, double* __restrict__ K)
@@ -76,6 +146,56 @@ __global__ void __launch_bounds__(256) build_cov_lower_kernel(const BlockSpec sp
 	}
 }
 
+/// One row of K* by one warp: lane l takes the column pairs 2 l, 2 l + 64, ...; returns the lane's share of the fused mean.
+/// FAST: fast_kernel_value, no coincidence term (valid unless `track` trips); else the exact evaluation.
+template <bool FAST>
+__device__ __forceinline__ double kstar_row(const BlockSpec& spec, const int rb, const double2 xq, const double2* __restrict__ Xt, const int N, const int Np, const int col_limit, const double* __restrict__ w, double* __restrict__ out, const int lane, const double* __restrict__ etab, unsigned& track)
+{
+	double acc = 0.0;
+	for (int cb = 0; cb < spec.nb; cb++)
+	{
+		const GaussBlock g = spec.b[rb][cb];
+		const double* __restrict__ wb = w + cb * Np;
+		double* __restrict__ ob = out + cb * Np;
+		const int jend = min(Np, col_limit - cb * Np); // col_limit is a multiple of 128
+		const int jpair = min(jend, N & ~1);		   // column pairs that are training points both
+		int j = lane * 2;
+#pragma unroll 4
+		for (; j < jpair; j += 64) // no bounds checks, no branches: ptxas interleaves the unrolled pairs
+		{
+			const double4 x = *reinterpret_cast<const double4*>(Xt + j);
+			const double2 wv = *reinterpret_cast<const double2*>(wb + j);
+			double2 val;
+			if (FAST)
+			{
+				val.x = fast_kernel_value(g, xq, make_double2(x.x, x.y), etab, track);
+				val.y = fast_kernel_value(g, xq, make_double2(x.z, x.w), etab, track);
+			}
+			else
+			{
+				bool same;
+				val.x = exact_kernel_value(g, xq, make_double2(x.x, x.y), same);
+				val.y = exact_kernel_value(g, xq, make_double2(x.z, x.w), same);
+			}
+			acc += val.x * wv.x;
+			acc += val.y * wv.y;
+			*reinterpret_cast<double2*>(ob + j) = val;
+		}
+		for (; j < jend; j += 64) // the odd last training point and the padding columns
+		{
+			double2 val = make_double2(0.0, 0.0);
+			if (j < N)
+			{
+				bool same;
+				val.x = FAST ? fast_kernel_value(g, xq, Xt[j], etab, track) : exact_kernel_value(g, xq, Xt[j], same);
+				acc += val.x * wb[j];
+			}
+			*reinterpret_cast<double2*>(ob + j) = val;
+		}
+	}
+	return acc;
+}
+
 /// Rows of the test-vs-training covariance for a chunk of `rows` composite rows starting at row0, written
 /// K-contiguous (row-major rows x n) as the A operand of the variance GEMM, fused with the mean K* v
 /// (kernel.cpp:495 / complex_kernel.cpp:608).  One warp per row; lanes stream 16-byte stores.
@@ -97,6 +217,8 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 	double* __restrict__ pred
 )
 {
+	__shared__ double etab[32];
+	load_exp_table(etab);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int r = blockIdx.x * 8 + warp;
 	if (r >= rows)
@@ -122,31 +244,15 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 		return;
 	}
 	const double2 xq = Xq[m];
+	unsigned track = fast_prefactor_ok(spec.b[rb][0]) && (spec.nb == 1 || fast_prefactor_ok(spec.b[rb][1])) ? 0u : 0xFFFFFFFFu;
 	double acc = 0.0;
-	for (int cb = 0; cb < spec.nb; cb++)
+	if (track == 0u)
 	{
-		const GaussBlock g = spec.b[rb][cb];
-		const double* __restrict__ wb = w + cb * Np;
-		double* __restrict__ ob = out + cb * Np;
-		const int jend = min(Np, col_limit - cb * Np); // col_limit is a multiple of 128
-#pragma unroll 4
-		for (int j = lane * 2; j < jend; j += 64)
-		{
-			double2 val = make_double2(0.0, 0.0);
-			if (j < N)
-			{
-				const double2 xa = Xt[j];
-				val.x = gauss_value(g, xq, xa) + ((xq.x == xa.x && xq.y == xa.y) ? g.diag_add : 0.0);
-				acc += val.x * wb[j];
-			}
-			if (j + 1 < N)
-			{
-				const double2 xb = Xt[j + 1];
-				val.y = gauss_value(g, xq, xb) + ((xq.x == xb.x && xq.y == xb.y) ? g.diag_add : 0.0);
-				acc += val.y * wb[j + 1];
-			}
-			*reinterpret_cast<double2*>(ob + j) = val;
-		}
+		acc = kstar_row<true>(spec, rb, xq, Xt, N, Np, col_limit, w, out, lane, etab, track);
+	}
+	if (__any_sync(0xffffffffu, track >= FAST_TRIP)) // a coincidence or an out-of-range exponent somewhere in the row: redo it exactly
+	{
+		acc = kstar_row<false>(spec, rb, xq, Xt, N, Np, col_limit, w, out, lane, etab, track);
 	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1)
@@ -167,7 +273,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(
 /// slots are combined by the xor butterfly), so a prediction is bit-identical whichever kernel produced it.
 /// `coincident[R]` = 1 when the query equals a training point (the delta term of kernel.cpp:8-31 fired).
 template <bool WARP_PER_ROW>
-__global__ void __launch_bounds__(256) kmean_kernel(
+__global__ void __launch_bounds__(256, WARP_PER_ROW ? 1 : 2) kmean_kernel(
 	const BlockSpec spec,
 	const double2* __restrict__ Xq,
 	const long long total_rows,
@@ -179,21 +285,24 @@ __global__ void __launch_bounds__(256) kmean_kernel(
 	unsigned char* __restrict__ coincident
 )
 {
-	constexpr int TJ = 256, ROWS = WARP_PER_ROW ? 8 : 256;
+	constexpr int TJ = 256, ROWS = WARP_PER_ROW ? 8 : 256, NACC = WARP_PER_ROW ? 1 : 32;
 	__shared__ double4 tile[TJ];
+	__shared__ double etab[32];
+	load_exp_table(etab);
 	const int lane = threadIdx.x & 31;
 	const long long R = (long long)blockIdx.x * ROWS + (WARP_PER_ROW ? threadIdx.x >> 5 : threadIdx.x);
 	const bool live = R < total_rows;
 	const long long m = live ? R / spec.nb : 0;
 	const int rb = int(live ? R - m * spec.nb : 0);
 	const double2 xq = Xq[m];
-	double acc[WARP_PER_ROW ? 1 : 32];
+	double acc[NACC];
 #pragma unroll
-	for (int i = 0; i < (WARP_PER_ROW ? 1 : 32); i++)
+	for (int i = 0; i < NACC; i++)
 	{
 		acc[i] = 0.0;
 	}
-	bool hit = false;
+	// fast pass (fast_kernel_value; see the comment at c_exp2_tab): no coincidence term, no special cases, only `track`
+	unsigned track = fast_prefactor_ok(spec.b[rb][0]) && (spec.nb == 1 || fast_prefactor_ok(spec.b[rb][1])) ? 0u : 0xFFFFFFFFu;
 	for (int cb = 0; cb < spec.nb; cb++)
 	{
 		const GaussBlock g = spec.b[rb][cb];
@@ -201,54 +310,72 @@ __global__ void __launch_bounds__(256) kmean_kernel(
 		{
 			__syncthreads();
 			{
+				// padding entries repeat the last training point with weight zero: they add exactly 0 to a sum and can only flag a
+				// coincidence that the real entry flags as well, so the loops below need no per-pair bounds check
 				const int j = j0 + threadIdx.x;
-				const double2 x = j < N ? Xt[j] : make_double2(0.0, 0.0);
+				const double2 x = Xt[min(j, N - 1)];
 				tile[threadIdx.x] = make_double4(x.x, x.y, j < N ? w[cb * Np + j] : 0.0, 0.0);
 			}
 			__syncthreads();
-			if (WARP_PER_ROW)
+			for (int k = 0; k < TJ / 64; k++)
 			{
-#pragma unroll
-				for (int k = 0; k < TJ / 64; k++)
+				if (j0 + 64 * k >= N)
+				{
+					break;
+				}
+				if (WARP_PER_ROW)
 				{
 #pragma unroll
 					for (int u = 0; u < 2; u++)
 					{
-						const int j = 64 * k + 2 * lane + u;
-						if (j0 + j < N)
-						{
-							const double4 t = tile[j];
-							const bool same = xq.x == t.x && xq.y == t.y;
-							hit |= same;
-							const double val = gauss_value(g, xq, make_double2(t.x, t.y)) + (same ? g.diag_add : 0.0);
-							acc[0] += val * t.z;
-						}
+						const double4 t = tile[64 * k + 2 * lane + u];
+						acc[0] += fast_kernel_value(g, xq, make_double2(t.x, t.y), etab, track) * t.z;
 					}
 				}
-			}
-			else
-			{
-				for (int k = 0; k < TJ / 64; k++)
+				else
 				{
-					if (j0 + 64 * k >= N)
-					{
-						break;
-					}
 #pragma unroll
 					for (int sl = 0; sl < 32; sl++)
 					{
 #pragma unroll
 						for (int u = 0; u < 2; u++)
 						{
-							const int j = 64 * k + 2 * sl + u;
-							if (j0 + j < N)
-							{
-								const double4 t = tile[j];
-								const bool same = xq.x == t.x && xq.y == t.y;
-								hit |= same;
-								const double val = gauss_value(g, xq, make_double2(t.x, t.y)) + (same ? g.diag_add : 0.0);
-								acc[sl] += val * t.z;
-							}
+							const double4 t = tile[64 * k + 2 * sl + u];
+							acc[sl < NACC ? sl : 0] += fast_kernel_value(g, xq, make_double2(t.x, t.y), etab, track) * t.z;
+						}
+					}
+				}
+			}
+		}
+	}
+	// exact pass for the flagged rows (a coincidence or an out-of-range exponent somewhere in the row), same summation order,
+	// training points straight from global memory (no barrier may sit inside a divergent region)
+	bool hit = false;
+	if (WARP_PER_ROW ? __any_sync(0xffffffffu, track >= FAST_TRIP) : track >= FAST_TRIP)
+	{
+#pragma unroll
+		for (int i = 0; i < NACC; i++)
+		{
+			acc[i] = 0.0;
+		}
+		for (int cb = 0; cb < spec.nb; cb++)
+		{
+			const GaussBlock g = spec.b[rb][cb];
+			const double* __restrict__ wb = w + cb * Np;
+			for (int jb = 0; jb < N; jb += 64)
+			{
+#pragma unroll
+				for (int sl = 0; sl < NACC; sl++)
+				{
+#pragma unroll
+					for (int u = 0; u < 2; u++)
+					{
+						const int j = jb + 2 * (WARP_PER_ROW ? lane : sl) + u;
+						if (j < N)
+						{
+							bool same;
+							acc[sl] += exact_kernel_value(g, xq, Xt[j], same) * wb[j];
+							hit |= same;
 						}
 					}
 				}
@@ -275,7 +402,7 @@ __global__ void __launch_bounds__(256) kmean_kernel(
 #pragma unroll
 			for (int i = 0; i < o; i++)
 			{
-				acc[i] += acc[i + o];
+				acc[i < NACC ? i : 0] += acc[i + o < NACC ? i + o : 0];
 			}
 		}
 		total = acc[0];
