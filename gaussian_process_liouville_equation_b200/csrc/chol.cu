@@ -47,29 +47,33 @@ __device__ __forceinline__ void named_barrier(const int id, const int count)
 	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-/// X_ii = L_ii^-1 of one 8 x 8 diagonal block by forward substitution, lane b (< 8) owning column b; the reciprocal pivots
-/// come from the factorisation.  Stored with the rest of X: X[a][b] (a >= b) = S[b][a + 1].
+/// X_ii = L_ii^-1 of one 8 x 8 diagonal block by forward substitution, lane b (< 8) owning column b, column-oriented (once
+/// x[a] is final every later row gets its fma: 8 x (mul, independent fmas)); the reciprocal pivots come from the factorisation.
+/// Stored with the rest of X: X[a][b] (a >= b) = S[b][a + 1].  The stores are UNCONDITIONAL: a lane-dependent store is a
+/// divergent branch (1475 cycles for eight of them, profiles/r02_leaf_latency.md); the zeros of a < b land in the lower
+/// triangle of the diagonal tile of S, which nobody reads during the sweep (the factor is parked in Ld and copied back at the end).
 __device__ __forceinline__ void inverse_diagonal_block(double* __restrict__ S, const double* __restrict__ Lb, const double* __restrict__ rs, const int i, const int b)
 {
 	double x[FW];
 #pragma unroll
 	for (int a = 0; a < FW; a++)
 	{
-		double v = 0.0;
-#pragma unroll
-		for (int k = 0; k < a; k++)
-		{
-			v = fma(-Lb[a * FW + k], x[k], v); // x[k] == 0 for k < b
-		}
-		x[a] = a == b ? rs[a] : (a > b ? v * rs[a] : 0.0);
+		x[a] = a == b ? 1.0 : 0.0; // right-hand side e_b
 	}
 #pragma unroll
 	for (int a = 0; a < FW; a++)
 	{
-		if (a >= b)
+		x[a] *= rs[a];
+#pragma unroll
+		for (int k = a + 1; k < FW; k++)
 		{
-			S[(i * FW + b) * LP + i * FW + a + 1] = x[a];
+			x[k] = fma(-Lb[k * FW + a], x[a], x[k]);
 		}
+	}
+#pragma unroll
+	for (int a = 0; a < FW; a++)
+	{
+		S[(i * FW + b) * LP + i * FW + a + 1] = x[a];
 	}
 }
 
