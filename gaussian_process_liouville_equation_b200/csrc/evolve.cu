@@ -350,7 +350,11 @@ __global__ void __launch_bounds__(256) evolve_post_kernel(const int model, doubl
 	}
 	else
 	{
-		rho_out[k] = make_double2(result.re, result.im);
+		// new_point_predict (evolve.cpp:434-442) returns 0 where is_coupling is false.  With CouplingCriterion == 0 that only happens
+		// where the criterion itself is NaN (e.g. Tully's SAC beyond |x| ~ 27, where V01 underflows and the adiabatic forces are
+		// 0 / 0): the reference reports an exact 0 there, which is_very_small counts as "small", not a NaN
+		const bool couple = is_coupling(adiabatic(model, x0), p0, mass, dt);
+		rho_out[k] = couple ? make_double2(result.re, result.im) : make_double2(0.0, 0.0);
 	}
 }
 

@@ -77,6 +77,22 @@ def test_new_point_predict_parity(dyn, oracle):
         assert np.abs(a - b).max() <= 1e-5 * scale
 
 
+def test_new_point_predict_far_from_the_crossing_is_exactly_zero(dyn, oracle):
+    """beyond |x| ~ 27 Tully's SAC coupling underflows, the adiabatic forces are 0 / 0 and is_coupling (evolve.cpp:53-100)
+    is false because its criterion is NaN: new_point_predict returns an exact 0 there (evolve.cpp:434-442), so that is_very_small
+    (evolve.cpp:445-470) sees a small value and not a NaN.  Points near the crossing in the same call are untouched."""
+    n, centre = 100, (-0.8, syn.P0)
+    sets, g = build_models(n, centre, False)
+    o0 = oracle.TrainingKernel(syn.theta_real(), *sets[0])
+    r = np.ascontiguousarray(sets[0][0][:8])
+    r[1::2, 0] = [28.0, -30.0, 35.0, 40.0]
+    for row, col in ((1, 0), (1, 1)):
+        a = dyn.new_point_predict(0, r, syn.MASS, 2.0, g, row, col)
+        b = oracle.new_point_predict(0, r, syn.MASS, 2.0, row, col, o0, None, None)
+        assert np.all(a[1::2] == 0.0) and np.all(b[1::2] == 0.0)
+        assert np.all(np.isfinite(a)) and np.abs(a[0::2] - b[0::2]).max() <= 1e-9 * max(np.abs(b).max(), 1e-300)
+
+
 def test_observables_parity(dyn, oracle):
     X, y = syn.training_set(11, 2, 100000, centre=(0.3, syn.P0))
     pts = syn.points_aos(X, y)

@@ -104,3 +104,69 @@ def test_cpp_optimiser_three_elements(tmp_path):
     for e, npar in enumerate((4, 8, 4)):
         assert all(np.isfinite(got[f"theta{e}_{p}"]) for p in range(npar))
     assert got["steps0"] > 0 and got["steps1"] > 0 and got["steps2"] > 0 and got["steps4"] > 0
+
+
+@pytest.mark.gpu
+def test_cpp_optimiser_outcome_at_n300_is_verified_by_the_oracle_and_locally_optimal(tmp_path):
+    """C3-shaped run (DAC, three populated elements, N = 300, M = 5 N) through the C++ host on the GPU, checked three ways
+    (the 20 % asserts of the small test say nothing):
+      1. the CPU oracle, evaluated at the returned parameters, reproduces the reported averages (1e-7 relative) and loss (1e-4):
+         the optimiser did not converge on a numerical artefact of the CUDA path;
+      2. the constraints hold far inside AverageTolerance (opt.h:13): population, energy and purity within 1e-3 of their targets;
+      3. a different constrained optimiser (scipy SLSQP on the Python mirror of the callbacks) started from the returned point
+         inside a +-25 % box finds no feasible point whose loss is more than 1 % lower: the point is a constrained local minimum."""
+    import oracle_backend
+    from scipy.optimize import minimize
+
+    from gaussian_process_liouville_equation_b200 import opt, predict
+
+    n, centre, dac = 300, (0.0, syn.P0), 1
+    density, extra = [], []
+    for e in range(3):
+        X, y = syn.training_set(35, e, n, centre)
+        Xe, ye = syn.extra_points(35, e, X, 5 * n, centre)
+        density.append(syn.points_aos(X, y))
+        extra.append(syn.points_aos(Xe, ye))
+    o = [oracle_backend.observable_sums(dac, density[e], syn.MASS, i) for i, e in enumerate((0, 2))]
+    energies = np.array([o[0][7] / o[0][0], o[1][7] / o[1][0]])
+    e0, purity0 = 0.6 * energies[0] + 0.4 * energies[1], syn.snapshot_purity()
+    got = run_cpp(density, extra, dac, e0, purity0, str(tmp_path), 300, 2000)
+    x = np.array([got[f"theta{e}_{p}"] for e, npar in enumerate((4, 8, 4)) for p in range(npar)])
+    assert np.all(np.isfinite(x)) and np.isfinite(got["error"])
+    # 2. constraints
+    assert abs(got["population"] - 1.0) < 1e-3 and abs(got["energy"] / e0 - 1.0) < 1e-3 and abs(got["purity"] / purity0 - 1.0) < 1e-3
+    # 1. the oracle at the returned point (the magnitudes were re-derived after the optimisation, opt.cpp:1179-1195: the averages
+    # are reported with them; the loss was minimised at InitialMagnitude)
+    ts, ets = predict.construct_training_sets(density), predict.construct_training_sets(extra)
+    k = predict.TrainingKernels([x[sl] for sl in predict.ELEMENT_SLICES], ts, False, True, False, oracle_backend)
+    assert abs(k.calculate_population() / got["population"] - 1.0) < 1e-7
+    assert abs(k.calculate_total_energy_average(energies) / got["energy"] - 1.0) < 1e-7
+    assert abs(k.calculate_purity() / got["purity"] - 1.0) < 1e-7
+    x_opt = x.copy()
+    for sl in predict.ELEMENT_SLICES:
+        x_opt[sl.start] = opt.InitialMagnitude
+    cb_oracle = opt.Callbacks(ts, ets, energies, e0, purity0, oracle_backend)
+    loss_oracle = cb_oracle.full_loose(x_opt)
+    # (1e-4: the reported error is the minimum the constrained stage saw, the parameters are its final iterate -- 2.7e-5 apart here)
+    assert abs(loss_oracle / got["error"] - 1.0) < 1e-4, (loss_oracle, got["error"])
+    # 3. SLSQP polish on the GPU-backed Python callbacks: magnitudes and noises stay fixed, the rest may move by 25 %
+    cb = opt.Callbacks(ts, ets, energies, e0, purity0)
+    fixed = np.zeros(16, dtype=bool)
+    for sl, npar in zip(predict.ELEMENT_SLICES, (4, 8, 4)):
+        fixed[sl.start] = fixed[sl.start + npar - 1] = True
+    free = ~fixed
+
+    def embed(z):
+        v = x_opt.copy()
+        v[free] = z
+        return v
+
+    def f(z):
+        v, g = cb.full_loose(embed(z), True)
+        return v, g[free]
+
+    cons = dict(type="eq", fun=lambda z: cb.full_constraints(embed(z), False), jac=lambda z: cb.full_constraints(embed(z), True)[1][:, free])
+    z0 = x_opt[free]
+    res = minimize(f, z0, jac=True, method="SLSQP", bounds=list(zip(0.8 * z0, 1.25 * z0)), constraints=[cons], options=dict(ftol=1e-12, maxiter=60))
+    feasible = np.abs(cb.full_constraints(embed(res.x), False)).max() < 1e-3
+    assert not (feasible and res.fun < 0.99 * got["error"]), (res.fun, got["error"], res.x / z0)
