@@ -1,5 +1,6 @@
 // Shared declarations of the B200 (sm_100a) GPR-MQCLE library: context, device buffers, status plumbing.
 #pragma once
+#include <mutex>
 #include "../../include/gple_b200.h"
 
 #include <cuda_runtime.h>
@@ -87,8 +88,10 @@ struct BlockPool
 {
 	std::multimap<size_t, void*> free_blocks;
 	std::map<void*, size_t> sizes;
+	std::mutex lock; // a model is freed by whichever thread drops the last reference to it
 	void* alloc(size_t bytes)
 	{
+		const std::lock_guard<std::mutex> guard(lock);
 		bytes = round_up(bytes == 0 ? 1 : bytes, 512);
 		auto it = free_blocks.lower_bound(bytes);
 		if (it != free_blocks.end() && it->first <= bytes + bytes / 4)
@@ -106,6 +109,7 @@ struct BlockPool
 	{
 		if (p != nullptr)
 		{
+			const std::lock_guard<std::mutex> guard(lock);
 			free_blocks.emplace(sizes.at(p), p);
 		}
 	}
