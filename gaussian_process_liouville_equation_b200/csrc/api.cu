@@ -235,6 +235,7 @@ extern "C"
 				GPLE_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
 				GPLE_CUDA(cudaEventCreateWithFlags(&ctx->ev_panel, cudaEventDisableTiming));
 				GPLE_CUDA(cudaEventCreateWithFlags(&ctx->ev_bulk, cudaEventDisableTiming));
+				GPLE_CUDA(cudaEventCreateWithFlags(&ctx->ev_graph, cudaEventDisableTiming));
 				ctx->stream = ctx->own_stream;
 				ctx->h_pinned_count = 512;
 				GPLE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pinned), ctx->h_pinned_count * sizeof(double)));
@@ -293,6 +294,14 @@ extern "C"
 			cudaEventDestroy(ctx->ev_panel);
 			cudaEventDestroy(ctx->ev_bulk);
 		}
+		for (auto& g : ctx->factorise_graph_cache)
+		{
+			cudaGraphExecDestroy(g.exec);
+		}
+		if (ctx->ev_graph != nullptr)
+		{
+			cudaEventDestroy(ctx->ev_graph);
+		}
 		if (ctx->own_stream != nullptr)
 		{
 			cudaStreamDestroy(ctx->own_stream);
@@ -325,6 +334,11 @@ extern "C"
 		if (option == GPLE_OPT_REFINE_SOLUTION)
 		{
 			ctx->refine_solution = value != 0;
+			return GPLE_OK;
+		}
+		if (option == GPLE_OPT_FACTORISE_GRAPHS)
+		{
+			ctx->factorise_graphs = value != 0;
 			return GPLE_OK;
 		}
 		if (option == GPLE_OPT_GATE_STAGE_TILES && value >= -1)

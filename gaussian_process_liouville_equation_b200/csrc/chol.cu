@@ -850,19 +850,119 @@ void potrf_trtri(gple_ctx* ctx, double* A, double* W, const int n, int* d_info)
 	const size_t ld = size_t(n);
 	double* dinv = ctx->ws.get<double>("chol.dinv", size_t(n / LEAF) * LEAF * LEAF);
 	double* T = ctx->ws.get<double>("chol.T", size_t(n / 2 + LEAF) * size_t(n / 2 + LEAF));
-	GPLE_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
-	const Chol c{ctx, A, ld, dinv, d_info};
-	c.potrf(0, n);
-	if (n > LEAF)
+	auto enqueue = [&]()
 	{
-		GPLE_LAUNCH(ctx, zero_upper_blocks_kernel, dim3(n / LEAF, n / LEAF), 256, 0, A, ld, n);
-	}
-	if (W != nullptr)
+		GPLE_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
+		const Chol c{ctx, A, ld, dinv, d_info};
+		c.potrf(0, n);
+		if (n > LEAF)
+		{
+			GPLE_LAUNCH(ctx, zero_upper_blocks_kernel, dim3(n / LEAF, n / LEAF), 256, 0, A, ld, n);
+		}
+		if (W != nullptr)
+		{
+			GPLE_CUDA(cudaMemsetAsync(W, 0, size_t(n) * n * sizeof(double), ctx->stream));
+			GPLE_LAUNCH(ctx, copy_dinv_kernel, n / LEAF, 256, 0, dinv, W, ld);
+			c.trtri(W, T);
+		}
+	};
+	// CUDA graph: at the sizes where the factorisation is a chain of short launches (a 128-leaf is 39 us, the GEMMs between two
+	// leaves 10-30 us, the look-ahead crosses streams through events) the whole schedule is captured once per (size, buffers) --
+	// the workspace and the model pool hand out the same buffers evaluation after evaluation -- and replayed with one launch.
+	if (!ctx->factorise_graphs || n > 8192 || n <= LEAF || ctx->own_stream == nullptr)
 	{
-		GPLE_CUDA(cudaMemsetAsync(W, 0, size_t(n) * n * sizeof(double), ctx->stream));
-		GPLE_LAUNCH(ctx, copy_dinv_kernel, n / LEAF, 256, 0, dinv, W, ld);
-		c.trtri(W, T);
+		enqueue();
+		return;
 	}
+	gple_ctx::FactoriseGraph* hit = nullptr;
+	for (auto& g : ctx->factorise_graph_cache)
+	{
+		if (g.n == n && g.A == A && g.W == W && g.info == d_info && g.dinv == dinv && g.T == T && g.potrf_flat == g_potrf_flat)
+		{
+			hit = &g;
+			break;
+		}
+	}
+	cudaStream_t user = ctx->stream, own = ctx->own_stream;
+	if (hit == nullptr)
+	{
+		// capture on the context's own stream (the caller's may be the legacy default stream, which cannot capture); relaxed
+		// mode: other host threads of this process keep calling the runtime for their own contexts
+		const unsigned long long before = ctx->launches;
+		cudaGraph_t graph = nullptr;
+		if (cudaStreamBeginCapture(own, cudaStreamCaptureModeRelaxed) != cudaSuccess)
+		{
+			cudaGetLastError();
+			enqueue();
+			return;
+		}
+		ctx->stream = own;
+		try
+		{
+			enqueue();
+		}
+		catch (...)
+		{
+			ctx->stream = user;
+			cudaStreamEndCapture(own, &graph);
+			if (graph != nullptr)
+			{
+				cudaGraphDestroy(graph);
+			}
+			throw;
+		}
+		ctx->stream = user;
+		GPLE_CUDA(cudaStreamEndCapture(own, &graph));
+		gple_ctx::FactoriseGraph g;
+		g.n = n;
+		g.A = A;
+		g.W = W;
+		g.info = d_info;
+		g.dinv = dinv;
+		g.T = T;
+		g.potrf_flat = g_potrf_flat;
+		g.launches = ctx->launches - before;
+		const cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+		cudaGraphDestroy(graph);
+		if (e != cudaSuccess)
+		{
+			cudaGetLastError();
+			ctx->launches = before;
+			enqueue();
+			return;
+		}
+		ctx->launches = before;
+		if (ctx->factorise_graph_cache.size() >= 12) // least used out
+		{
+			size_t worst = 0;
+			for (size_t i = 1; i < ctx->factorise_graph_cache.size(); i++)
+			{
+				if (ctx->factorise_graph_cache[i].uses < ctx->factorise_graph_cache[worst].uses)
+				{
+					worst = i;
+				}
+			}
+			cudaGraphExecDestroy(ctx->factorise_graph_cache[worst].exec);
+			ctx->factorise_graph_cache.erase(ctx->factorise_graph_cache.begin() + long(worst));
+		}
+		ctx->factorise_graph_cache.push_back(g);
+		hit = &ctx->factorise_graph_cache.back();
+		ctx->graph_captures++;
+	}
+	if (user != own)
+	{
+		GPLE_CUDA(cudaEventRecord(ctx->ev_graph, user));
+		GPLE_CUDA(cudaStreamWaitEvent(own, ctx->ev_graph, 0));
+	}
+	GPLE_CUDA(cudaGraphLaunch(hit->exec, own));
+	if (user != own)
+	{
+		GPLE_CUDA(cudaEventRecord(ctx->ev_graph, own));
+		GPLE_CUDA(cudaStreamWaitEvent(user, ctx->ev_graph, 0));
+	}
+	hit->uses++;
+	ctx->launches += hit->launches;
+	ctx->graph_replays++;
 }
 
 } // namespace gple

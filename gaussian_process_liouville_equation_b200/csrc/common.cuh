@@ -147,6 +147,19 @@ struct gple_ctx
 	// bound-gated variance (GPLE_OPT_GATED_VARIANCE) and its statistics
 	bool gated_variance = true;
 	bool refine_solution = true; // GPLE_OPT_REFINE_SOLUTION
+	// CUDA graphs of the factorisation (potrf + trtri: ~100 short dependent launches on two streams), one per (size, buffers)
+	bool factorise_graphs = true; // GPLE_OPT_FACTORISE_GRAPHS
+	struct FactoriseGraph
+	{
+		int n = 0;
+		const void *A = nullptr, *W = nullptr, *info = nullptr, *dinv = nullptr, *T = nullptr;
+		int potrf_flat = 0;
+		cudaGraphExec_t exec = nullptr;
+		unsigned long long launches = 0, uses = 0;
+	};
+	std::vector<FactoriseGraph> factorise_graph_cache;
+	cudaEvent_t ev_graph = nullptr;
+	unsigned long long graph_replays = 0, graph_captures = 0;
 	int gate_stage_tiles = -1;	  // GPLE_OPT_GATE_STAGE_TILES (-1: automatic)
 	int gate_stage_tiles_im = -1; // GPLE_OPT_GATE_STAGE_TILES_IM (-1: automatic)
 	unsigned long long gate_rows_total = 0, gate_rows_variance = 0, gate_rows_zero = 0, gate_rows_stage_b = 0;

@@ -85,7 +85,11 @@ extern "C"
 		/* (default 1) one step of iterative refinement of v = K^-1 y' after the factorisation (residual against the regenerated
 		 * covariance): v at the accuracy of the reference's LDLT solve (kernel.cpp:281-284) instead of that of the explicit
 		 * triangular inverse; 0 only for measuring the difference (tests/test_gpu_baseline_sizes.py) */
-		GPLE_OPT_REFINE_SOLUTION = 4
+		GPLE_OPT_REFINE_SOLUTION = 4,
+		/* (default 1) the factorisation (Cholesky + triangular inverse: about a hundred short, dependent launches on two streams at
+		 * n = 2048) is captured once per (size, buffers) into a CUDA graph and replayed: the launch-bound inner loop of every model
+		 * rebuild and of every loss evaluation of the optimiser.  Same kernels, same results; 0 for measuring the difference. */
+		GPLE_OPT_FACTORISE_GRAPHS = 5
 	};
 	int gple_ctx_set_option(gple_ctx* ctx, int option, int value);
 	/* Gated predictions since the last call (then reset): out = {composite rows seen, rows sent through stage A of the

@@ -231,3 +231,28 @@ def test_factorisation_schedules_on_ragged_block_counts(gk, n):
     probe = np.random.default_rng(n).standard_normal((n, 8))
     assert np.abs(K @ (Kinv @ probe) - probe).max() <= 1e-7 * np.abs(probe).max()
     assert k.get_error() == pytest.approx(float(np.sum((v / np.diag(Kinv)) ** 2)), rel=1e-9)
+
+
+def test_factorisation_as_a_cuda_graph_changes_nothing(gk):
+    """GPLE_OPT_FACTORISE_GRAPHS (default on): the factorisation schedule replayed from a captured CUDA graph launches the same
+    kernels on the same buffers as the direct launches -- every scalar, v and a prediction bit for bit, over alternating sizes
+    (one cached graph per size and buffer set) and repeated evaluations (the optimiser's pattern)."""
+    from gaussian_process_liouville_equation_b200 import _lib as L
+
+    ctx = L.default_context()
+    out = {}
+    for graphs in (True, False):
+        ctx.set_factorise_graphs(graphs)
+        try:
+            res = []
+            for n in (300, 700, 300, 1100, 700, 300):
+                X, y = syn.training_set(5, 0, n)
+                k = gk.TrainingKernel(syn.theta_real(), (X, y), True, True, False)
+                p = gk.PredictiveKernel(X[:50] + 0.01, k)
+                res.append((k.get_error(), k.get_population(), k.get_purity(), p.get_prediction().copy(), p.get_variance().copy()))
+            out[graphs] = res
+        finally:
+            ctx.set_factorise_graphs(True)
+    for a, b in zip(out[True], out[False]):
+        assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+        assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
