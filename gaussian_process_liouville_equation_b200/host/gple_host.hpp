@@ -13,6 +13,7 @@
 #pragma once
 #include "../../include/gple_b200.h"
 
+#include <cstdint>
 #include <algorithm>
 #include <array>
 #include <cassert>
@@ -710,10 +711,32 @@ public:
 	std::size_t misses() const { return Misses; }
 
 private:
+	/// An entry is keyed by the ADDRESS of the training set (the callbacks of one optimisation pass the same object again and
+	/// again) plus a fingerprint of its CONTENT -- size and every feature / label value folded into 64 bits -- so that a
+	/// different set that happens to live at a recycled address can never be served a stale model
+	static std::uint64_t fingerprint(const ElementTrainingSet& ts)
+	{
+		std::uint64_t h = 1469598103934665603ull;
+		auto fold = [&h](const void* p, const std::size_t bytes)
+		{
+			const unsigned char* c = static_cast<const unsigned char*>(p);
+			for (std::size_t i = 0; i < bytes; i++)
+			{
+				h = (h ^ c[i]) * 1099511628211ull;
+			}
+		};
+		const auto& [X, y] = ts;
+		const std::size_t n = X.cols();
+		fold(&n, sizeof(n));
+		fold(X.data(), 2 * n * sizeof(double));
+		fold(y.data(), y.size() * sizeof(std::complex<double>));
+		return h;
+	}
 	template <typename K>
 	struct Entry
 	{
 		const ElementTrainingSet* key;
+		std::uint64_t print;
 		ParameterVector theta;
 		unsigned flags;
 		std::shared_ptr<const K> model;
@@ -727,11 +750,12 @@ private:
 	std::shared_ptr<const K> get(std::vector<Entry<K>>& entries, const ElementTrainingSet& ts, const ParameterVector& theta, const bool err, const bool avg, const bool deriv)
 	{
 		const unsigned want = (err ? 1u : 0u) | (avg ? 2u : 0u) | (deriv ? 4u : 0u);
+		const std::uint64_t print = fingerprint(ts);
 		{
 			const std::lock_guard<std::mutex> lock(Mutex);
 			for (const auto& e : entries)
 			{
-				if (e.key == &ts && e.theta == theta && (e.flags & want) == want)
+				if (e.key == &ts && e.print == print && e.theta == theta && (e.flags & want) == want)
 				{
 					Hits++;
 					return e.model;
@@ -746,11 +770,11 @@ private:
 		{
 			if (e.key == &ts)
 			{
-				e = Entry<K>{&ts, theta, want, model};
+				e = Entry<K>{&ts, print, theta, want, model};
 				return model;
 			}
 		}
-		entries.push_back(Entry<K>{&ts, theta, want, model});
+		entries.push_back(Entry<K>{&ts, print, theta, want, model});
 		return model;
 	}
 };
