@@ -1327,18 +1327,34 @@ int train_common(gple_ctx* ctx, gple_model* m, const BlockSpec& spec, const Devi
 		GPLE_LAUNCH(ctx, col_pass_kernel, dim3(n / 128, nslab), 128, 0, m->W, n, Np, 0, z, slab, part);
 		GPLE_LAUNCH(ctx, refine_add_kernel, (n + 255) / 256, 256, 0, part, n, nslab, m->v);
 	}
-	int h_info = 0;
-	GPLE_CUDA(cudaMemcpyAsync(&h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
-	return h_info == 0 ? GPLE_OK : GPLE_ERR_NOT_SPD;
+	return GPLE_OK; // nothing has been waited for: the pivot status comes back with the scalars (finish_train)
 }
 
-double quadform(gple_ctx* ctx, const gple_model* m, const QuadSpec& qs, const double* w, double* d_out)
+/// The ONE host synchronisation of a training call: the first `count` scalars and the factorisation's pivot status.
+/// Returns GPLE_OK or GPLE_ERR_NOT_SPD.
+int finish_train(gple_ctx* ctx, const double* d_scal, const int count, double* h)
+{
+	const int* d_info = ctx->ws.get<int>("train.info", 4);
+	GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_scal, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 64, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
+	std::memcpy(h, ctx->h_pinned, count * sizeof(double));
+	int info = 0;
+	std::memcpy(&info, ctx->h_pinned + 64, sizeof(int));
+	return info == 0 ? GPLE_OK : GPLE_ERR_NOT_SPD;
+}
+
+/// w^T K1 w into *d_out, enqueued only
+void quadform_enqueue(gple_ctx* ctx, const gple_model* m, const QuadSpec& qs, const double* w, double* d_out)
 {
 	const int tiles = m->n / 128;
 	double* part = ctx->ws.get<double>("train.quadpart", size_t(tiles) * tiles);
 	GPLE_LAUNCH(ctx, quadform_kernel, dim3(tiles, tiles), 256, 0, qs, reinterpret_cast<const double2*>(m->X), int(m->N), m->Np, w, part);
 	GPLE_LAUNCH(ctx, sum_kernel, 1, 1024, 0, part, tiles * tiles, d_out);
+}
+double quadform(gple_ctx* ctx, const gple_model* m, const QuadSpec& qs, const double* w, double* d_out)
+{
+	quadform_enqueue(ctx, m, qs, w, d_out);
 	double h = 0.0;
 	read_scalars(ctx, d_out, 1, &h);
 	return h;
@@ -1431,10 +1447,17 @@ int train_real(gple_ctx* ctx, const double* X_, const double* y_, size_t N, cons
 	int status = GPLE_OK;
 	try
 	{
-		status = train_common(ctx, m, real_spec(theta), X, y, d_scal);
+		train_common(ctx, m, real_spec(theta), X, y, d_scal);
 		GPLE_LAUNCH(ctx, real_scalars_kernel, 1, 1024, 0, reinterpret_cast<const double2*>(m->X), m->label, m->v, m->kinv_diag, int(N), d_scal);
+		if (flags & GPLE_CALC_AVERAGE)
+		{
+			QuadSpec qs{};
+			qs.nb = 1;
+			qs.g[0][0][0] = aux_block(theta[0], theta[1], theta[2], 1.0);
+			quadform_enqueue(ctx, m, qs, m->v, d_scal + 8);
+		}
 		double h[SCAL_COUNT];
-		read_scalars(ctx, d_scal, 8, h);
+		status = finish_train(ctx, d_scal, 9, h); // the one synchronisation of the call
 		m->rescale = h[0];
 		const double nan = std::nan("");
 		gple_real_scalars r{};
@@ -1453,10 +1476,7 @@ int train_real(gple_ctx* ctx, const double* X_, const double* y_, size_t N, cons
 			r.population = f * h[2] / r.rescale;	   // kernel.cpp:286-297
 			r.first_order[0] = f * h[3] / r.rescale; // kernel.cpp:298-312
 			r.first_order[1] = f * h[4] / r.rescale;
-			QuadSpec qs{};
-			qs.nb = 1;
-			qs.g[0][0][0] = aux_block(theta[0], theta[1], theta[2], 1.0);
-			const double quad = quadform(ctx, m, qs, m->v, d_scal + 8);
+			const double quad = h[8];
 			r.purity = (2.0 * M_PI) * M_PI * quad / (r.rescale * r.rescale); // kernel.cpp:325-335
 		}
 		if (flags & GPLE_CALC_DERIVATIVE)
@@ -1497,21 +1517,8 @@ int train_complex(gple_ctx* ctx, const double* X_, const double* y_, size_t N, c
 	int status = GPLE_OK;
 	try
 	{
-		status = train_common(ctx, m, complex_spec(theta), X, y, d_scal);
+		train_common(ctx, m, complex_spec(theta), X, y, d_scal);
 		GPLE_LAUNCH(ctx, complex_scalars_kernel, 1, 1024, 0, m->label, m->v, m->kinv_diag, m->kinv_diag + m->n, int(N), m->Np, d_scal);
-		double h[SCAL_COUNT];
-		read_scalars(ctx, d_scal, 8, h);
-		m->rescale = h[0];
-		const double nan = std::nan("");
-		gple_complex_scalars r{};
-		r.rescale = h[0];
-		r.error = (flags & GPLE_CALC_ERROR) ? h[1] : nan;
-		r.magnitude = std::sqrt(std::fabs(h[2] / double(N))); // complex_kernel.h:192-204
-		r.purity = nan;
-		for (int p = 0; p < 8; p++)
-		{
-			r.d_error[p] = r.d_purity[p] = nan;
-		}
 		if (flags & GPLE_CALC_AVERAGE)
 		{
 			// complex_kernel.cpp:357-377 with v = (wr + i wi) / 2:
@@ -1525,7 +1532,24 @@ int train_complex(gple_ctx* ctx, const double* X_, const double* y_, size_t N, c
 			qs.g[1][1][1] = aux_block(c.sc, c.lc[0], c.lc[1], 1.0);
 			qs.g[0][1][0] = qs.g[1][0][0] = mixed_block(c.sr, c.lr, c.sc, c.lc, 1.0);
 			qs.g[0][1][1] = qs.g[1][0][1] = mixed_block(c.si, c.li, c.sc, c.lc, 1.0);
-			const double quad = 0.5 * quadform(ctx, m, qs, m->v, d_scal + 8);
+			quadform_enqueue(ctx, m, qs, m->v, d_scal + 8);
+		}
+		double h[SCAL_COUNT];
+		status = finish_train(ctx, d_scal, 9, h); // the one synchronisation of the call
+		m->rescale = h[0];
+		const double nan = std::nan("");
+		gple_complex_scalars r{};
+		r.rescale = h[0];
+		r.error = (flags & GPLE_CALC_ERROR) ? h[1] : nan;
+		r.magnitude = std::sqrt(std::fabs(h[2] / double(N))); // complex_kernel.h:192-204
+		r.purity = nan;
+		for (int p = 0; p < 8; p++)
+		{
+			r.d_error[p] = r.d_purity[p] = nan;
+		}
+		if (flags & GPLE_CALC_AVERAGE)
+		{
+			const double quad = 0.5 * h[8];
 			const double s4 = theta[0] * theta[0] * theta[0] * theta[0];
 			r.purity = (2.0 * M_PI) * 2.0 * M_PI * s4 * quad / (r.rescale * r.rescale);
 		}
