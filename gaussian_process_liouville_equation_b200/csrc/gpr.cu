@@ -32,9 +32,9 @@ namespace
 // 8 Q N exponentials per element and step and are bound by the FP64 pipe, which DFMA shares with DMMA on B200
 // (profiles/r02_kstar_fusion_decision.md), so what counts is the number of FP64 instructions per kernel value -- and, right
 // behind it, the number of instructions of any kind (one issue slot per cycle and scheduler against two cycles per FP64
-// instruction).  The library exp() spends about 17 FP64 instructions (degree-11 polynomial); this one 11:
+// instruction).  The library exp() spends about 17 FP64 instructions (degree-11 polynomial); this one 12:
 //   k = rint(-s * 16 / ln 2),  exp(-s / 2) = 2^(k >> 5) * T[k & 31] * exp(r),  T[j] = 2^(j / 32) from shared memory (32 x 8 bytes:
-//   at most a two-way bank conflict),  |r| <= ln 2 / 64,  degree-6 Taylor polynomial (remainder 3.5e-18);
+//   at most a two-way bank conflict),  |r| <= ln 2 / 64,  degree-6 Taylor polynomial (remainder 3.5e-18) in Estrin form;
 // the power of two goes into the exponent field of the prefactor sigma_f^2 on the integer pipe, so that scaling and prefactor
 // are ONE multiplication.  Error <= 2 ulp.  The hot loop carries no special cases at all: it only tracks, per row, whether
 // some s was exactly zero (a query that coincides with a training point: the delta term of kernel.cpp:8-31) or outside
@@ -79,11 +79,13 @@ __device__ __forceinline__ double fast_kernel_value(const GaussBlock& g, const d
 	const double kf = t - 6755399441055744.0;
 	double r = fma(kf, 0x1.62e42fee00000p-5, s); // r = s + k * (2 ln 2 / 32) = -2 * (reduced argument); the product is exact
 	r = fma(kf, 0x1.a39ef35793c76p-37, r);
-	double p = fma(0x1.6c16c16c16c17p-16, r, -0x1.1111111111111p-12); // sum_n (-1/2)^n r^n / n!
-	p = fma(p, r, 0x1.5555555555555p-9);
-	p = fma(p, r, -0x1.5555555555555p-6);
-	p = fma(p, r, 0x1.0000000000000p-3);
-	p = fma(p, r, -0.5);
+	// sum_n (-1/2)^n r^(n-1) / n!, n = 1 .. 6, by Estrin's scheme: three dependent levels instead of Horner's five (the loop is
+	// bound by the latency between dependent FP64 instructions, ncu: stall `wait`), one multiplication more
+	const double r2 = r * r;
+	const double pa = fma(0x1.0000000000000p-3, r, -0.5);
+	const double pb = fma(0x1.5555555555555p-9, r, -0x1.5555555555555p-6);
+	const double pc = fma(0x1.6c16c16c16c17p-16, r, -0x1.1111111111111p-12);
+	const double p = fma(fma(pc, r2, pb), r2, pa);
 	const double T = tab[k & 31];
 	const double v = fma(T, p * r, T);
 	// sigma_f^2 * 2^(k >> 5): (k >> 5) << 20 == (k << 15) & 0xFFF00000 added to the high word (k <= 0; no carry out of the field)
