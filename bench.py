@@ -303,6 +303,8 @@ def run_ours(args):
         ctx.comm_init(rank, world, box[0])
     if args.gate_stage_tiles is not None:
         ctx.set_gate_stage_tiles(args.gate_stage_tiles, args.gate_stage_tiles_im)
+    if args.gate_stage2_tiles is not None:
+        ctx.set_gate_stage2_tiles(args.gate_stage2_tiles)
     lib = ctx.lib
     # the three element models of a step are independent: they are factorised concurrently, one context (stream +
     # workspace) per element, from three host threads (the C-ABI is thread-safe across contexts)
@@ -512,6 +514,7 @@ def main():
     ap.add_argument("--north-star-points", type=int, default=1_000_000)
     ap.add_argument("--gate-stage-tiles", type=int, default=None, help="override GPLE_OPT_GATE_STAGE_TILES (tuning)")
     ap.add_argument("--gate-stage-tiles-im", type=int, default=-1, help="override GPLE_OPT_GATE_STAGE_TILES_IM (tuning)")
+    ap.add_argument("--gate-stage2-tiles", type=int, default=None, help="override GPLE_OPT_GATE_STAGE2_TILES (tuning; 0 = stage B in one part)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2 (default, BASELINE.json configs[1]); c4 = configs[3]: ECR, N=4096, 1e6 evolved points/element, meant for --gpus 8")
     args = ap.parse_args()
     if args.workload == "c4":

@@ -162,6 +162,9 @@ class Context:
     def set_factorise_graphs(self, on: bool):
         self.check(self.lib.gple_ctx_set_option(self.h, 5, int(on)))
 
+    def set_gate_stage2_tiles(self, tiles: int):
+        self.check(self.lib.gple_ctx_set_option(self.h, 6, int(tiles)))
+
     def set_gate_stage_tiles(self, tiles: int, tiles_im: int = -1):
         self.check(self.lib.gple_ctx_set_option(self.h, 2, int(tiles)))
         self.check(self.lib.gple_ctx_set_option(self.h, 3, int(tiles_im)))

@@ -346,6 +346,11 @@ extern "C"
 			ctx->gate_stage_tiles = value;
 			return GPLE_OK;
 		}
+		if (option == GPLE_OPT_GATE_STAGE2_TILES && value >= -1)
+		{
+			ctx->gate_stage2_tiles = value;
+			return GPLE_OK;
+		}
 		if (option == GPLE_OPT_GATE_STAGE_TILES_IM && value >= -1)
 		{
 			ctx->gate_stage_tiles_im = value;

@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const double* __restrict_
 /// Second stage of the gate: q1 = sum Z^2 over the stage-A tile set gives var <= k** - q1, so |f|^2 >= 4 (k** - q1) decides
 /// gate == 1 exactly.  One thread per listed query (nb consecutive list entries).  slot2[entry] = -1 (decided) or the
 /// entry's position in the stage-B list idx2 (original composite rows).  counter[2] = stage-B rows.
-__global__ void __launch_bounds__(256) classify2_kernel(const double* __restrict__ pred, const int* __restrict__ idx1, const double* __restrict__ q1, const int queries, const int nb, const double prior, int* __restrict__ idx2, int* __restrict__ slot2, int* __restrict__ counter)
+__global__ void __launch_bounds__(256) classify2_kernel(const double* __restrict__ pred, const int* __restrict__ idx1, const double* __restrict__ q1, const int queries, const int nb, const double prior, int* __restrict__ idx2, int* __restrict__ slot2, int* __restrict__ back2, int* __restrict__ counter)
 {
 	const int e = blockIdx.x * 256 + threadIdx.x;
 	bool need = false;
@@ -702,6 +702,50 @@ __global__ void __launch_bounds__(256) classify2_kernel(const double* __restrict
 			if (need)
 			{
 				idx2[mine + k] = idx1[e * nb + k];
+				if (back2 != nullptr)
+				{
+					back2[mine + k] = e * nb + k; // where this entry's stage-A sum sits
+				}
+			}
+		}
+	}
+}
+
+/// Third stage of the gate: after the first part of the remaining tiles (stage B1) the bound is var <= k** - q1 - q2; the
+/// queries it decides (gate == 1) skip the long products of the last tiles (stage B2).  One thread per stage-B1 query.
+/// slot3[entry] = -1 (decided) or the entry's position in the stage-B2 list idx3.  counter[3] = stage-B2 rows.
+__global__ void __launch_bounds__(256) classify3_kernel(const double* __restrict__ pred, const int* __restrict__ idx2, const int* __restrict__ back2, const double* __restrict__ q1, const double* __restrict__ q2, const int queries, const int nb, const double prior, int* __restrict__ idx3, int* __restrict__ slot3, int* __restrict__ counter)
+{
+	const int e = blockIdx.x * 256 + threadIdx.x;
+	bool need = false;
+	if (e < queries)
+	{
+		double f2 = 0.0, qs = 0.0;
+		for (int k = 0; k < nb; k++)
+		{
+			const double f = pred[idx2[e * nb + k]];
+			f2 = fma(f, f, f2);
+			qs += q1[back2[e * nb + k]] + q2[e * nb + k];
+		}
+		need = !(f2 >= 4.0 * (prior - qs)); // NaN keeps the full path
+	}
+	const unsigned ballot = __ballot_sync(0xffffffffu, need);
+	const int lane = threadIdx.x & 31;
+	int base = 0;
+	if (lane == 0 && ballot != 0u)
+	{
+		base = atomicAdd(counter + 3, __popc(ballot) * nb);
+	}
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (e < queries)
+	{
+		const int mine = base + __popc(ballot & ((1u << lane) - 1u)) * nb;
+		for (int k = 0; k < nb; k++)
+		{
+			slot3[e * nb + k] = need ? mine + k : -1;
+			if (need)
+			{
+				idx3[mine + k] = idx2[e * nb + k];
 			}
 		}
 	}
@@ -721,7 +765,7 @@ __device__ __forceinline__ double gate_factor(const double pred_sq, const double
 	return (5.0 - 2.0 * a) * (a - 1.0) * (a - 1.0);
 }
 
-__global__ void finalize_real_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int* __restrict__ slot2, const double* __restrict__ q2, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double* __restrict__ pred_out, double* __restrict__ var_out, double* __restrict__ cut_out)
+__global__ void finalize_real_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int* __restrict__ slot2, const double* __restrict__ q2, const int* __restrict__ slot3, const double* __restrict__ q3, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double* __restrict__ pred_out, double* __restrict__ var_out, double* __restrict__ cut_out)
 {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= rows || row0 + r >= Q)
@@ -732,8 +776,10 @@ __global__ void finalize_real_kernel(const double* __restrict__ pred, const doub
 	const int sl = slot != nullptr ? slot[r] : r;
 	// sl < 0: gate decided by a bound (classify_kernel); s2 == -1: decided 1 by the stage-A bound (classify2_kernel)
 	const int s2 = (sl >= 0 && slot2 != nullptr) ? slot2[sl] : 0;
-	const double var = sl >= 0 ? prior - q[sl] - ((slot2 != nullptr && s2 >= 0) ? q2[s2] : 0.0) : prior;
-	const double gate = sl >= 0 ? (s2 == -1 ? 1.0 : gate_factor(f * f, fabs(f), var)) : (sl == -1 ? 1.0 : 0.0);
+	// s3 == -1: decided 1 by the stage-B1 bound (classify3_kernel)
+	const int s3 = (sl >= 0 && s2 >= 0 && slot3 != nullptr) ? slot3[s2] : 0;
+	const double var = sl >= 0 ? prior - q[sl] - ((slot2 != nullptr && s2 >= 0) ? q2[s2] : 0.0) - ((slot3 != nullptr && s2 >= 0 && s3 >= 0) ? q3[s3] : 0.0) : prior;
+	const double gate = sl >= 0 ? ((s2 == -1 || s3 == -1) ? 1.0 : gate_factor(f * f, fabs(f), var)) : (sl == -1 ? 1.0 : 0.0);
 	if (pred_out != nullptr)
 	{
 		pred_out[row0 + r] = f;
@@ -749,7 +795,7 @@ __global__ void finalize_real_kernel(const double* __restrict__ pred, const doub
 }
 
 /// complex_kernel.cpp:608-643 in composite form: rows (2m, 2m+1) = (Re, Im) parts of query m
-__global__ void finalize_complex_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int* __restrict__ slot2, const double* __restrict__ q2, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double2* __restrict__ pred_out, double* __restrict__ var_out, double2* __restrict__ cut_out)
+__global__ void finalize_complex_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int* __restrict__ slot2, const double* __restrict__ q2, const int* __restrict__ slot3, const double* __restrict__ q3, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double2* __restrict__ pred_out, double* __restrict__ var_out, double2* __restrict__ cut_out)
 {
 	const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
 	const long long m = row0 / 2 + pidx;
@@ -760,9 +806,10 @@ __global__ void finalize_complex_kernel(const double* __restrict__ pred, const d
 	const double fr = pred[2 * pidx], fi = pred[2 * pidx + 1];
 	const int sl = slot != nullptr ? slot[2 * pidx] : 2 * pidx;
 	const int s2 = (sl >= 0 && slot2 != nullptr) ? slot2[sl] : 0;
-	const double var = sl >= 0 ? prior - q[sl] - q[sl + 1] - ((slot2 != nullptr && s2 >= 0) ? q2[s2] + q2[s2 + 1] : 0.0) : prior;
+	const int s3 = (sl >= 0 && s2 >= 0 && slot3 != nullptr) ? slot3[s2] : 0;
+	const double var = sl >= 0 ? prior - q[sl] - q[sl + 1] - ((slot2 != nullptr && s2 >= 0) ? q2[s2] + q2[s2 + 1] : 0.0) - ((slot3 != nullptr && s2 >= 0 && s3 >= 0) ? q3[s3] + q3[s3 + 1] : 0.0) : prior;
 	const double ps = fr * fr + fi * fi;
-	const double gate = sl >= 0 ? (s2 == -1 ? 1.0 : gate_factor(ps, hypot(fr, fi), var)) : (sl == -1 ? 1.0 : 0.0);
+	const double gate = sl >= 0 ? ((s2 == -1 || s3 == -1) ? 1.0 : gate_factor(ps, hypot(fr, fi), var)) : (sl == -1 ? 1.0 : 0.0);
 	if (pred_out != nullptr)
 	{
 		pred_out[m] = make_double2(fr, fi);
@@ -1637,7 +1684,16 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		const TileSet full{0, T, 0, 0};
 		const int stage_im = std::min(ctx->gate_stage_tiles_im >= 0 ? ctx->gate_stage_tiles_im : std::max(1, stage / 4), Th);
 		const TileSet setA = !staged ? full : (m->is_complex ? TileSet{0, stage, Th, stage_im} : TileSet{0, stage, 0, 0});
+		// Stage B in two parts: B1 = the next blocks of (Re) rows up to `stage2` (short products still), then -- for the queries whose
+		// bound k** - sum Z^2 over A and B1 still does not decide the gate -- B2 = everything else (the long products, and all
+		// remaining Im tiles of the complex element).  The tighter bound decides another fifth of the stage-B queries before the
+		// long products: 11.4 % -> 9.2 % of the rows need the full variance on the C2 workload, step 187 -> 171 ms.
+		// automatic: five eighths of the blocks (profiles/r02_gate_three_stages.md: 10 of 16 at N = 2048)
+		const int stage2 = !staged ? Th : std::min(Th, ctx->gate_stage2_tiles >= 0 ? std::max(stage, ctx->gate_stage2_tiles) : std::max(stage + 1, 5 * Th / 8));
+		const bool split_b = staged && stage2 > stage && stage2 < Th;
 		const TileSet setB = m->is_complex ? TileSet{stage, Th - stage, Th + stage_im, Th - stage_im} : TileSet{stage, T - stage, 0, 0};
+		const TileSet setB1 = TileSet{stage, stage2 - stage, 0, 0};
+		const TileSet setB2 = m->is_complex ? TileSet{stage2, Th - stage2, Th + stage_im, Th - stage_im} : TileSet{stage2, T - stage2, 0, 0};
 		double* q = ctx->ws.get<double>("pred.q_all", round_up(size_t(count), 128) + size_t(CHUNK_ROWS) * MAX_VAR_SPLITS);
 		auto sweep = [&](const int* list, const int list_count, const TileSet& ts, double* qout)
 		{
@@ -1656,21 +1712,39 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 			}
 		};
 		sweep(gate_idx, count, setA, q);
-		int* slot2 = nullptr;
-		double* q2 = nullptr;
+		int *slot2 = nullptr, *slot3 = nullptr;
+		double *q2 = nullptr, *q3 = nullptr;
 		if (staged)
 		{
 			// ---- stage B: only the queries the stage-A bound does not decide see the remaining tiles
 			int* idx2 = ctx->ws.get<int>("pred.gate_idx2", round_up(size_t(count), 128));
 			slot2 = ctx->ws.get<int>("pred.gate_slot2", round_up(size_t(count), 128));
-			GPLE_LAUNCH(ctx, classify2_kernel, unsigned((count / nb + 255) / 256), 256, 0, pred, gate_idx, q, count / nb, nb, m->prior, idx2, slot2, gate_cnt);
+			int* back2 = split_b ? ctx->ws.get<int>("pred.gate_back2", round_up(size_t(count), 128)) : nullptr;
+			GPLE_LAUNCH(ctx, classify2_kernel, unsigned((count / nb + 255) / 256), 256, 0, pred, gate_idx, q, count / nb, nb, m->prior, idx2, slot2, back2, gate_cnt);
 			GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 204, gate_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 			GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
 			int count2 = 0;
 			std::memcpy(&count2, ctx->h_pinned + 204, sizeof(int));
-			ctx->gate_rows_stage_b += (unsigned long long)count2;
 			q2 = ctx->ws.get<double>("pred.q2_all", round_up(size_t(count2), 128) + size_t(CHUNK_ROWS) * MAX_VAR_SPLITS);
-			sweep(idx2, count2, setB, q2);
+			if (!split_b || count2 == 0)
+			{
+				ctx->gate_rows_stage_b += (unsigned long long)count2;
+				sweep(idx2, count2, setB, q2);
+			}
+			else
+			{
+				sweep(idx2, count2, setB1, q2);
+				int* idx3 = ctx->ws.get<int>("pred.gate_idx3", round_up(size_t(count2), 128));
+				slot3 = ctx->ws.get<int>("pred.gate_slot3", round_up(size_t(count2), 128));
+				GPLE_LAUNCH(ctx, classify3_kernel, unsigned((count2 / nb + 255) / 256), 256, 0, pred, idx2, back2, q, q2, count2 / nb, nb, m->prior, idx3, slot3, gate_cnt);
+				GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 206, gate_cnt + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+				GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
+				int count3 = 0;
+				std::memcpy(&count3, ctx->h_pinned + 206, sizeof(int));
+				ctx->gate_rows_stage_b += (unsigned long long)count3; // rows that needed the full variance
+				q3 = ctx->ws.get<double>("pred.q3_all", round_up(size_t(count3), 128) + size_t(CHUNK_ROWS) * MAX_VAR_SPLITS);
+				sweep(idx3, count3, setB2, q3);
+			}
 		}
 		else
 		{
@@ -1678,11 +1752,11 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		}
 		if (m->is_complex)
 		{
-			GPLE_LAUNCH(ctx, finalize_complex_kernel, unsigned((total_rows / 2 + 255) / 256), 256, 0, pred, q, gate_slot, slot2, q2, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
+			GPLE_LAUNCH(ctx, finalize_complex_kernel, unsigned((total_rows / 2 + 255) / 256), 256, 0, pred, q, gate_slot, slot2, q2, slot3, q3, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
 		}
 		else
 		{
-			GPLE_LAUNCH(ctx, finalize_real_kernel, unsigned((total_rows + 255) / 256), 256, 0, pred, q, gate_slot, slot2, q2, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
+			GPLE_LAUNCH(ctx, finalize_real_kernel, unsigned((total_rows + 255) / 256), 256, 0, pred, q, gate_slot, slot2, q2, slot3, q3, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
 		}
 		if (d_err != nullptr && d_yq != nullptr)
 		{
@@ -1718,11 +1792,11 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		}
 		if (m->is_complex)
 		{
-			GPLE_LAUNCH(ctx, finalize_complex_kernel, (rows / 2 + 255) / 256, 256, 0, pred, q, nullptr, nullptr, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
+			GPLE_LAUNCH(ctx, finalize_complex_kernel, (rows / 2 + 255) / 256, 256, 0, pred, q, nullptr, nullptr, nullptr, nullptr, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
 		}
 		else
 		{
-			GPLE_LAUNCH(ctx, finalize_real_kernel, (rows + 255) / 256, 256, 0, pred, q, nullptr, nullptr, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
+			GPLE_LAUNCH(ctx, finalize_real_kernel, (rows + 255) / 256, 256, 0, pred, q, nullptr, nullptr, nullptr, nullptr, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
 		}
 		if (d_err != nullptr && d_yq != nullptr)
 		{

@@ -89,7 +89,11 @@ extern "C"
 		/* (default 1) the factorisation (Cholesky + triangular inverse: about a hundred short, dependent launches on two streams at
 		 * n = 2048) is captured once per (size, buffers) into a CUDA graph and replayed: the launch-bound inner loop of every model
 		 * rebuild and of every loss evaluation of the optimiser.  Same kernels, same results; 0 for measuring the difference. */
-		GPLE_OPT_FACTORISE_GRAPHS = 5
+		GPLE_OPT_FACTORISE_GRAPHS = 5,
+		/* staged gate, second boundary (default -1 = five eighths of the training blocks): the queries the stage-A bound leaves open
+		 * first see the blocks [stage, stage2) only; the tighter bound decides another fifth of them before the long products of
+		 * the last blocks.  A value <= the stage runs the rest in one part (round-1 schedule). */
+		GPLE_OPT_GATE_STAGE2_TILES = 6
 	};
 	int gple_ctx_set_option(gple_ctx* ctx, int option, int value);
 	/* Gated predictions since the last call (then reset): out = {composite rows seen, rows sent through stage A of the
