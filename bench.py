@@ -44,6 +44,16 @@ WORKLOAD = ("C2: Tully SAC, N=2048 training points/element, 3 elements (rho00,rh
             "step = TrainingKernels rebuild (3 elements) + evolve (8Q GPR predictions per element)")
 
 
+def parse_schedule(text):
+    """'1,5,10' or '1:0,5:1,10:2' -> [(re_end, im_end), ...] (cumulative 128-blocks)."""
+    out = []
+    for item in text.split(","):
+        if item.strip():
+            a, _, b = item.partition(":")
+            out.append((int(a), int(b) if b else 0))
+    return out
+
+
 def make_inputs():
     sets = [syn.training_set(2, e, N_TRAIN, CENTRE) for e in range(3)]
     pts = []
@@ -305,6 +315,10 @@ def run_ours(args):
         ctx.set_gate_stage_tiles(args.gate_stage_tiles, args.gate_stage_tiles_im)
     if args.gate_stage2_tiles is not None:
         ctx.set_gate_stage2_tiles(args.gate_stage2_tiles)
+    if args.gate_schedule_real is not None:
+        ctx.set_gate_schedule(False, parse_schedule(args.gate_schedule_real))
+    if args.gate_schedule_complex is not None:
+        ctx.set_gate_schedule(True, parse_schedule(args.gate_schedule_complex))
     lib = ctx.lib
     # the three element models of a step are independent: they are factorised concurrently, one context (stream +
     # workspace) per element, from three host threads (the C-ABI is thread-safe across contexts)
@@ -515,6 +529,8 @@ def main():
     ap.add_argument("--gate-stage-tiles", type=int, default=None, help="override GPLE_OPT_GATE_STAGE_TILES (tuning)")
     ap.add_argument("--gate-stage-tiles-im", type=int, default=-1, help="override GPLE_OPT_GATE_STAGE_TILES_IM (tuning)")
     ap.add_argument("--gate-stage2-tiles", type=int, default=None, help="override GPLE_OPT_GATE_STAGE2_TILES (tuning; 0 = stage B in one part)")
+    ap.add_argument("--gate-schedule-real", default=None, help="explicit schedule of the staged bound, real elements: e.g. 1,5,10 (tuning)")
+    ap.add_argument("--gate-schedule-complex", default=None, help="same for the complex element, re:im pairs: e.g. 1:0,5:1,10:2,16:6 (tuning)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2 (default, BASELINE.json configs[1]); c4 = configs[3]: ECR, N=4096, 1e6 evolved points/element, meant for --gpus 8")
     args = ap.parse_args()
     if args.workload == "c4":

@@ -51,6 +51,7 @@ SIGNATURES = {
     "gple_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "gple_ctx_sync": (C.c_int, [_vp]),
     "gple_ctx_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "gple_ctx_set_gate_schedule": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "gple_gate_statistics": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
     "gple_last_error": (C.c_char_p, [_vp]),
     "gple_launch_count": (C.c_ulonglong, [_vp]),
@@ -164,6 +165,13 @@ class Context:
 
     def set_gate_stage2_tiles(self, tiles: int):
         self.check(self.lib.gple_ctx_set_option(self.h, 6, int(tiles)))
+
+    def set_gate_schedule(self, complex_element: bool, stages):
+        """stages: sequence of cumulative (re_end, im_end) block boundaries (128 training points each); empty = automatic."""
+        st = [(int(s), 0) if np.isscalar(s) else (int(s[0]), int(s[1])) for s in stages]
+        re = (C.c_int * max(1, len(st)))(*[s[0] for s in st])
+        im = (C.c_int * max(1, len(st)))(*[s[1] for s in st])
+        self.check(self.lib.gple_ctx_set_gate_schedule(self.h, int(bool(complex_element)), len(st), C.cast(re, C.c_void_p), C.cast(im, C.c_void_p)))
 
     def set_gate_stage_tiles(self, tiles: int, tiles_im: int = -1):
         self.check(self.lib.gple_ctx_set_option(self.h, 2, int(tiles)))

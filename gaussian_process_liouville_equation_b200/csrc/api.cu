@@ -359,6 +359,27 @@ extern "C"
 		return GPLE_ERR_ARG;
 	}
 
+	int gple_ctx_set_gate_schedule(gple_ctx* ctx, int complex_element, int stages, const int* re_end, const int* im_end)
+	{
+		if (ctx == nullptr || stages < 0 || stages > 15 || (stages > 0 && re_end == nullptr))
+		{
+			return GPLE_ERR_ARG;
+		}
+		std::vector<int> flat;
+		for (int k = 0; k < stages; k++)
+		{
+			const int im = im_end != nullptr ? im_end[k] : 0;
+			if (re_end[k] < 0 || im < 0)
+			{
+				return GPLE_ERR_ARG;
+			}
+			flat.push_back(re_end[k]);
+			flat.push_back(im);
+		}
+		ctx->gate_schedule[complex_element != 0 ? 1 : 0] = flat;
+		return GPLE_OK;
+	}
+
 	int gple_gate_statistics(gple_ctx* ctx, unsigned long long out[4])
 	{
 		if (ctx == nullptr || out == nullptr)

@@ -162,7 +162,8 @@ struct gple_ctx
 	unsigned long long graph_replays = 0, graph_captures = 0;
 	int gate_stage_tiles = -1;	  // GPLE_OPT_GATE_STAGE_TILES (-1: automatic)
 	int gate_stage_tiles_im = -1; // GPLE_OPT_GATE_STAGE_TILES_IM (-1: automatic)
-	int gate_stage2_tiles = -1;	  // GPLE_OPT_GATE_STAGE2_TILES (-1: automatic = twice the stage; <= stage: stage B in one part)
+	std::vector<int> gate_schedule[2]; // gple_ctx_set_gate_schedule: (re_end, im_end) pairs, [0] real / [1] complex element; empty: automatic
+	int gate_stage2_tiles = -1;	  // GPLE_OPT_GATE_STAGE2_TILES (with an explicit stage: -1 = five eighths of the blocks)
 	unsigned long long gate_rows_total = 0, gate_rows_variance = 0, gate_rows_zero = 0, gate_rows_stage_b = 0;
 	// optional per-kernel event timing (gple_profile_*)
 	bool prof_on = false;

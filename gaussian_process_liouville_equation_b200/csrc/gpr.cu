@@ -458,7 +458,7 @@ struct TileSet
 };
 
 template <typename C>
-__global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* __restrict__ A, const double* __restrict__ W, const int n, double* __restrict__ part, const int rows, const TileSet ts)
+__global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* __restrict__ A, const int lda, const double* __restrict__ W, const int n, double* __restrict__ part, const int rows, const TileSet ts)
 {
 	using namespace gemm;
 	extern __shared__ __align__(16) double smem[];
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 	static_assert(C::BM == 128 && C::BN == 128, "the variance GEMM walks 128-wide n-tiles");
 	const int m0 = blockIdx.x * BM;
 	const int V = ts.count();
-	const double* Ag = A + size_t(m0) * n;
+	const double* Ag = A + size_t(m0) * lda;
 	// When a chunk has fewer than ~148 row blocks the n-tiles are dealt round-robin to gridDim.y CTAs per row
 	// block (interleaving balances the triangular work).  Whatever the deal, every (n-tile, column-warp) pair writes its
 	// own partial row sums to part[(v * WARPS_N + wn)][rows]; var_reduce_kernel adds them in that fixed order, so a row's
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) var_gemm_kernel(const double* _
 	{
 		if (l_v < V)
 		{
-			load_tile_kmajor<C, 128>(As + l_slot * C::A_STAGE, Ag + size_t(l_kt) * C::BK, size_t(n), tid);
+			load_tile_kmajor<C, 128>(As + l_slot * C::A_STAGE, Ag + size_t(l_kt) * C::BK, size_t(lda), tid);
 			load_tile_kmajor<C, 128>(Bs + l_slot * C::B_STAGE, W + size_t(l_nt) * BN * n + size_t(l_kt) * C::BK, size_t(n), tid);
 			l_slot = (l_slot + 1 == C::STAGES) ? 0 : l_slot + 1;
 			if (++l_kt == (l_nt + 1) * (BN / C::BK))
@@ -565,7 +565,7 @@ constexpr int MAX_VAR_SPLITS = 16;
 int g_var_variant = 1; // BK = 32, 3 stages, 2 x 4 warps: 88.8 % of the DMMA peak on B200 (profiles/r01_tune_var_gemm.txt)
 
 template <typename C>
-void launch_var_gemm_cfg(gple_ctx* ctx, const double* A, const double* W, int n, int rows, double* q, const TileSet& ts)
+void launch_var_gemm_cfg(gple_ctx* ctx, const double* A, int lda, const double* W, int n, int rows, double* q, const TileSet& ts)
 {
 	// choose the number of n-splits S that minimises the makespan ceil(blocks * S / SMs) / S
 	const int mb = rows / 128, T = ts.count();
@@ -581,7 +581,7 @@ void launch_var_gemm_cfg(gple_ctx* ctx, const double* A, const double* W, int n,
 		}
 	}
 	double* part = ctx->ws.get<double>("pred.qpart", size_t(rows) * size_t(T) * C::WARPS_N);
-	GPLE_LAUNCH(ctx, var_gemm_kernel<C>, dim3(mb, best), C::THREADS, C::SMEM_BYTES, A, W, n, part, rows, ts);
+	GPLE_LAUNCH(ctx, var_gemm_kernel<C>, dim3(mb, best), C::THREADS, C::SMEM_BYTES, A, lda, W, n, part, rows, ts);
 	GPLE_LAUNCH(ctx, var_reduce_kernel, (rows + 255) / 256, 256, 0, part, q, rows, T * C::WARPS_N);
 }
 
@@ -591,24 +591,25 @@ double var_gemm_flops(const TileSet& ts, int rows)
 	return 2.0 * 128.0 * 128.0 * ts.weight() * double(rows);
 }
 
-void launch_var_gemm(gple_ctx* ctx, int variant, const double* A, const double* W, int n, int rows, double* q, const TileSet& ts)
+/// A: rows x (at least the columns the tile set reads), row pitch lda; W: the n x n lower-triangular inverse factor
+void launch_var_gemm(gple_ctx* ctx, int variant, const double* A, int lda, const double* W, int n, int rows, double* q, const TileSet& ts)
 {
 	switch (variant)
 	{
 	case 1:
-		return launch_var_gemm_cfg<VarCfg1>(ctx, A, W, n, rows, q, ts);
+		return launch_var_gemm_cfg<VarCfg1>(ctx, A, lda, W, n, rows, q, ts);
 	case 2:
-		return launch_var_gemm_cfg<VarCfg2>(ctx, A, W, n, rows, q, ts);
+		return launch_var_gemm_cfg<VarCfg2>(ctx, A, lda, W, n, rows, q, ts);
 	case 3:
-		return launch_var_gemm_cfg<VarCfg3>(ctx, A, W, n, rows, q, ts);
+		return launch_var_gemm_cfg<VarCfg3>(ctx, A, lda, W, n, rows, q, ts);
 	case 4:
-		return launch_var_gemm_cfg<VarCfg4>(ctx, A, W, n, rows, q, ts);
+		return launch_var_gemm_cfg<VarCfg4>(ctx, A, lda, W, n, rows, q, ts);
 	case 5:
-		return launch_var_gemm_cfg<VarCfg5>(ctx, A, W, n, rows, q, ts);
+		return launch_var_gemm_cfg<VarCfg5>(ctx, A, lda, W, n, rows, q, ts);
 	case 6:
-		return launch_var_gemm_cfg<VarCfg6>(ctx, A, W, n, rows, q, ts);
+		return launch_var_gemm_cfg<VarCfg6>(ctx, A, lda, W, n, rows, q, ts);
 	default:
-		return launch_var_gemm_cfg<VarCfg0>(ctx, A, W, n, rows, q, ts);
+		return launch_var_gemm_cfg<VarCfg0>(ctx, A, lda, W, n, rows, q, ts);
 	}
 }
 
@@ -666,31 +667,34 @@ __global__ void __launch_bounds__(256) classify_kernel(const double* __restrict_
 	}
 }
 
-/// kernel.cpp:496-519 + kernel.h:301-332: variance, cubic gate, cutoff prediction (real element)
-/// Second stage of the gate: q1 = sum Z^2 over the stage-A tile set gives var <= k** - q1, so |f|^2 >= 4 (k** - q1) decides
-/// gate == 1 exactly.  One thread per listed query (nb consecutive list entries).  slot2[entry] = -1 (decided) or the
-/// entry's position in the stage-B list idx2 (original composite rows).  counter[2] = stage-B rows.
-__global__ void __launch_bounds__(256) classify2_kernel(const double* __restrict__ pred, const int* __restrict__ idx1, const double* __restrict__ q1, const int queries, const int nb, const double prior, int* __restrict__ idx2, int* __restrict__ slot2, int* __restrict__ back2, int* __restrict__ counter)
+/// A stage of the bound-gated variance: `qs` = sum Z^2 of the listed rows over this stage's tile set is added to the running
+/// per-row sum `qsum` (dense, indexed by composite row; assigned when `first`), and var <= k** - qsum decides gate == 1 exactly
+/// where |f|^2 >= 4 (k** - qsum).  One thread per listed query (nb consecutive list entries).  Decided rows get slot = -1; the
+/// rows of the others are compacted into `next` (composite rows); *counter = rows kept.
+__global__ void __launch_bounds__(256) classify_stage_kernel(const double* __restrict__ pred, const int* __restrict__ list, const double* __restrict__ qs, double* __restrict__ qsum, const int first, const int queries, const int nb, const double prior, int* __restrict__ next, int* __restrict__ slot, int* __restrict__ counter)
 {
 	const int e = blockIdx.x * 256 + threadIdx.x;
 	bool need = false;
 	if (e < queries)
 	{
-		double f2 = 0.0, qs = 0.0;
+		double f2 = 0.0, total = 0.0;
 		for (int k = 0; k < nb; k++)
 		{
-			const double f = pred[idx1[e * nb + k]];
+			const int r = list[e * nb + k];
+			const double f = pred[r];
 			f2 = fma(f, f, f2);
-			qs += q1[e * nb + k];
+			const double t = (first ? 0.0 : qsum[r]) + qs[e * nb + k];
+			qsum[r] = t;
+			total += t;
 		}
-		need = !(f2 >= 4.0 * (prior - qs)); // NaN keeps the full path
+		need = !(f2 >= 4.0 * (prior - total)); // NaN keeps the full path
 	}
 	const unsigned ballot = __ballot_sync(0xffffffffu, need);
 	const int lane = threadIdx.x & 31;
 	int base = 0;
 	if (lane == 0 && ballot != 0u)
 	{
-		base = atomicAdd(counter + 2, __popc(ballot) * nb);
+		base = atomicAdd(counter, __popc(ballot) * nb);
 	}
 	base = __shfl_sync(0xffffffffu, base, 0);
 	if (e < queries)
@@ -698,56 +702,27 @@ __global__ void __launch_bounds__(256) classify2_kernel(const double* __restrict
 		const int mine = base + __popc(ballot & ((1u << lane) - 1u)) * nb;
 		for (int k = 0; k < nb; k++)
 		{
-			slot2[e * nb + k] = need ? mine + k : -1;
+			const int r = list[e * nb + k];
 			if (need)
 			{
-				idx2[mine + k] = idx1[e * nb + k];
-				if (back2 != nullptr)
-				{
-					back2[mine + k] = e * nb + k; // where this entry's stage-A sum sits
-				}
+				next[mine + k] = r;
+			}
+			else
+			{
+				slot[r] = -1;
 			}
 		}
 	}
 }
 
-/// Third stage of the gate: after the first part of the remaining tiles (stage B1) the bound is var <= k** - q1 - q2; the
-/// queries it decides (gate == 1) skip the long products of the last tiles (stage B2).  One thread per stage-B1 query.
-/// slot3[entry] = -1 (decided) or the entry's position in the stage-B2 list idx3.  counter[3] = stage-B2 rows.
-__global__ void __launch_bounds__(256) classify3_kernel(const double* __restrict__ pred, const int* __restrict__ idx2, const int* __restrict__ back2, const double* __restrict__ q1, const double* __restrict__ q2, const int queries, const int nb, const double prior, int* __restrict__ idx3, int* __restrict__ slot3, int* __restrict__ counter)
+/// Last stage: the listed rows have seen every tile; their sums are completed (the gate is then evaluated from the variance).
+__global__ void __launch_bounds__(256) accumulate_stage_kernel(const int* __restrict__ list, const double* __restrict__ qs, double* __restrict__ qsum, const int first, const int count)
 {
 	const int e = blockIdx.x * 256 + threadIdx.x;
-	bool need = false;
-	if (e < queries)
+	if (e < count)
 	{
-		double f2 = 0.0, qs = 0.0;
-		for (int k = 0; k < nb; k++)
-		{
-			const double f = pred[idx2[e * nb + k]];
-			f2 = fma(f, f, f2);
-			qs += q1[back2[e * nb + k]] + q2[e * nb + k];
-		}
-		need = !(f2 >= 4.0 * (prior - qs)); // NaN keeps the full path
-	}
-	const unsigned ballot = __ballot_sync(0xffffffffu, need);
-	const int lane = threadIdx.x & 31;
-	int base = 0;
-	if (lane == 0 && ballot != 0u)
-	{
-		base = atomicAdd(counter + 3, __popc(ballot) * nb);
-	}
-	base = __shfl_sync(0xffffffffu, base, 0);
-	if (e < queries)
-	{
-		const int mine = base + __popc(ballot & ((1u << lane) - 1u)) * nb;
-		for (int k = 0; k < nb; k++)
-		{
-			slot3[e * nb + k] = need ? mine + k : -1;
-			if (need)
-			{
-				idx3[mine + k] = idx2[e * nb + k];
-			}
-		}
+		const int r = list[e];
+		qsum[r] = (first ? 0.0 : qsum[r]) + qs[e];
 	}
 }
 
@@ -765,7 +740,8 @@ __device__ __forceinline__ double gate_factor(const double pred_sq, const double
 	return (5.0 - 2.0 * a) * (a - 1.0) * (a - 1.0);
 }
 
-__global__ void finalize_real_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int* __restrict__ slot2, const double* __restrict__ q2, const int* __restrict__ slot3, const double* __restrict__ q3, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double* __restrict__ pred_out, double* __restrict__ var_out, double* __restrict__ cut_out)
+/// kernel.cpp:496-519 + kernel.h:301-332: variance, cubic gate, cutoff prediction (real element)
+__global__ void finalize_real_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double* __restrict__ pred_out, double* __restrict__ var_out, double* __restrict__ cut_out)
 {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= rows || row0 + r >= Q)
@@ -773,13 +749,11 @@ __global__ void finalize_real_kernel(const double* __restrict__ pred, const doub
 		return;
 	}
 	const double f = pred[r];
-	const int sl = slot != nullptr ? slot[r] : r;
-	// sl < 0: gate decided by a bound (classify_kernel); s2 == -1: decided 1 by the stage-A bound (classify2_kernel)
-	const int s2 = (sl >= 0 && slot2 != nullptr) ? slot2[sl] : 0;
-	// s3 == -1: decided 1 by the stage-B1 bound (classify3_kernel)
-	const int s3 = (sl >= 0 && s2 >= 0 && slot3 != nullptr) ? slot3[s2] : 0;
-	const double var = sl >= 0 ? prior - q[sl] - ((slot2 != nullptr && s2 >= 0) ? q2[s2] : 0.0) - ((slot3 != nullptr && s2 >= 0 && s3 >= 0) ? q3[s3] : 0.0) : prior;
-	const double gate = sl >= 0 ? ((s2 == -1 || s3 == -1) ? 1.0 : gate_factor(f * f, fabs(f), var)) : (sl == -1 ? 1.0 : 0.0);
+	// slot (bound-gated schedule only): >= 0 the row went through every tile and q holds its sum Z^2; -1 / -2: the gate was decided
+	// 1 / 0 by a bound (classify_kernel, classify_stage_kernel)
+	const int sl = slot != nullptr ? slot[r] : 0;
+	const double var = sl >= 0 ? prior - q[r] : prior;
+	const double gate = sl >= 0 ? gate_factor(f * f, fabs(f), var) : (sl == -1 ? 1.0 : 0.0);
 	if (pred_out != nullptr)
 	{
 		pred_out[row0 + r] = f;
@@ -795,7 +769,7 @@ __global__ void finalize_real_kernel(const double* __restrict__ pred, const doub
 }
 
 /// complex_kernel.cpp:608-643 in composite form: rows (2m, 2m+1) = (Re, Im) parts of query m
-__global__ void finalize_complex_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int* __restrict__ slot2, const double* __restrict__ q2, const int* __restrict__ slot3, const double* __restrict__ q3, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double2* __restrict__ pred_out, double* __restrict__ var_out, double2* __restrict__ cut_out)
+__global__ void finalize_complex_kernel(const double* __restrict__ pred, const double* __restrict__ q, const int* __restrict__ slot, const int rows, const long long row0, const long long Q, const double prior, const double rescale, double2* __restrict__ pred_out, double* __restrict__ var_out, double2* __restrict__ cut_out)
 {
 	const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
 	const long long m = row0 / 2 + pidx;
@@ -804,12 +778,10 @@ __global__ void finalize_complex_kernel(const double* __restrict__ pred, const d
 		return;
 	}
 	const double fr = pred[2 * pidx], fi = pred[2 * pidx + 1];
-	const int sl = slot != nullptr ? slot[2 * pidx] : 2 * pidx;
-	const int s2 = (sl >= 0 && slot2 != nullptr) ? slot2[sl] : 0;
-	const int s3 = (sl >= 0 && s2 >= 0 && slot3 != nullptr) ? slot3[s2] : 0;
-	const double var = sl >= 0 ? prior - q[sl] - q[sl + 1] - ((slot2 != nullptr && s2 >= 0) ? q2[s2] + q2[s2 + 1] : 0.0) - ((slot3 != nullptr && s2 >= 0 && s3 >= 0) ? q3[s3] + q3[s3 + 1] : 0.0) : prior;
+	const int sl = slot != nullptr ? slot[2 * pidx] : 0;
+	const double var = sl >= 0 ? prior - q[2 * pidx] - q[2 * pidx + 1] : prior;
 	const double ps = fr * fr + fi * fi;
-	const double gate = sl >= 0 ? ((s2 == -1 || s3 == -1) ? 1.0 : gate_factor(ps, hypot(fr, fi), var)) : (sl == -1 ? 1.0 : 0.0);
+	const double gate = sl >= 0 ? gate_factor(ps, hypot(fr, fi), var) : (sl == -1 ? 1.0 : 0.0);
 	if (pred_out != nullptr)
 	{
 		pred_out[m] = make_double2(fr, fi);
@@ -1624,6 +1596,75 @@ int train_complex(gple_ctx* ctx, const double* X_, const double* y_, size_t N, c
 	return status;
 }
 
+/// One stage of the bound-gated variance: the tiles up to block `re_end` of the (Re) rows and up to block `im_end` of the Im
+/// rows (complex element; cumulative, in 128-blocks of training points).
+struct GateStage
+{
+	int re_end, im_end;
+};
+constexpr int MAX_GATE_STAGES = 16;
+
+/// The stages before the last one (which always completes the tile set).
+///  * gple_ctx_set_gate_schedule: explicit;
+///  * GPLE_OPT_GATE_STAGE_TILES >= 0: the round-1 / early round-2 schedule (0: single stage; t: [t (+ t/4 Im blocks)], then
+///    GPLE_OPT_GATE_STAGE2_TILES);
+///  * automatic: Re boundaries 1, 5, 17, 53, ... (b -> 3 b + 2) up to half of the blocks, then 21/32 of them: the first block
+///    alone decides more than half of the open queries for 1/136 of the full product, and each later boundary is placed where the
+///    rows it removes pay for the extra pass (dynamic programme over the measured survival curves, profiles/r02_gate_schedule.md).
+///    Complex element: no Im block in the first stage (an Im tile costs a product over ALL Re columns), then one Im block per
+///    five Re blocks, and a stage with all Re blocks and 3/8 of the Im blocks before the last one.
+std::vector<GateStage> gate_schedule(const gple_ctx* ctx, const bool is_complex, const int Th)
+{
+	std::vector<GateStage> raw;
+	const std::vector<int>& ex = ctx->gate_schedule[is_complex ? 1 : 0];
+	if (!ex.empty())
+	{
+		for (size_t k = 0; k + 1 < ex.size(); k += 2)
+		{
+			raw.push_back(GateStage{ex[k], ex[k + 1]});
+		}
+	}
+	else if (ctx->gate_stage_tiles >= 0)
+	{
+		const int stage = std::min(ctx->gate_stage_tiles, Th);
+		if (stage > 0 && stage < Th)
+		{
+			const int stage_im = std::min(ctx->gate_stage_tiles_im >= 0 ? ctx->gate_stage_tiles_im : std::max(1, stage / 4), Th);
+			raw.push_back(GateStage{stage, stage_im});
+			const int stage2 = ctx->gate_stage2_tiles >= 0 ? ctx->gate_stage2_tiles : std::max(stage + 1, 5 * Th / 8);
+			raw.push_back(GateStage{stage2, stage_im});
+		}
+	}
+	else
+	{
+		for (int b = 1; 2 * b <= Th; b = 3 * b + 2)
+		{
+			raw.push_back(GateStage{b, b == 1 ? 0 : std::max(1, b / 5)});
+		}
+		const int late = 21 * Th / 32;
+		raw.push_back(GateStage{late, std::max(1, late / 5)});
+		if (is_complex)
+		{
+			raw.push_back(GateStage{Th, std::max(1, 3 * Th / 8)});
+		}
+	}
+	// cumulative, strictly growing, and something left for the last stage
+	std::vector<GateStage> out;
+	const int Ti = is_complex ? Th : 0;
+	int re = 0, im = 0;
+	for (const GateStage& g : raw)
+	{
+		const int r1 = std::max(re, std::min(g.re_end, Th)), i1 = std::max(im, std::min(g.im_end, Ti));
+		if ((r1 > re || i1 > im) && (r1 < Th || i1 < Ti) && int(out.size()) < MAX_GATE_STAGES - 1)
+		{
+			out.push_back(GateStage{r1, i1});
+			re = r1;
+			im = i1;
+		}
+	}
+	return out;
+}
+
 /// Batched prediction of `Q` points on the device.  d_pred / d_cut hold nb doubles per point.
 ///
 /// Two schedules:
@@ -1672,91 +1713,76 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		ctx->gate_rows_total += (unsigned long long)total_rows;
 		ctx->gate_rows_variance += (unsigned long long)count;
 		ctx->gate_rows_zero += (unsigned long long)counts[1];
-		// ---- stage A: the listed rows against a small tile set (the first `stage` 128-blocks of training points: for the
-		// complex element the Re rows of those points plus their Im rows, which sit after all Re rows in the composite order).
-		// k** - sum Z^2 over a subset of Z's columns is the posterior variance given only those observations: an upper bound
-		// of the variance that is already close to the noise floor inside the point cloud.
-		const int T = n / 128, Th = m->is_complex ? T / 2 : T;
-		// automatic choice: a quarter of the training blocks, between 2 and 8; for the complex element a quarter as many blocks of
-		// Im rows (each of them costs a product over ALL Re columns, and they tighten the bound little) (profiles/r01_tune_gate_stage.md)
-		const int stage = std::min(ctx->gate_stage_tiles >= 0 ? ctx->gate_stage_tiles : std::max(2, std::min(8, Th / 4)), Th);
-		const bool staged = stage > 0 && stage < Th && count > 0;
-		const TileSet full{0, T, 0, 0};
-		const int stage_im = std::min(ctx->gate_stage_tiles_im >= 0 ? ctx->gate_stage_tiles_im : std::max(1, stage / 4), Th);
-		const TileSet setA = !staged ? full : (m->is_complex ? TileSet{0, stage, Th, stage_im} : TileSet{0, stage, 0, 0});
-		// Stage B in two parts: B1 = the next blocks of (Re) rows up to `stage2` (short products still), then -- for the queries whose
-		// bound k** - sum Z^2 over A and B1 still does not decide the gate -- B2 = everything else (the long products, and all
-		// remaining Im tiles of the complex element).  The tighter bound decides another fifth of the stage-B queries before the
-		// long products: 11.4 % -> 9.2 % of the rows need the full variance on the C2 workload, step 187 -> 171 ms.
-		// automatic: five eighths of the blocks (profiles/r02_gate_three_stages.md: 10 of 16 at N = 2048)
-		const int stage2 = !staged ? Th : std::min(Th, ctx->gate_stage2_tiles >= 0 ? std::max(stage, ctx->gate_stage2_tiles) : std::max(stage + 1, 5 * Th / 8));
-		const bool split_b = staged && stage2 > stage && stage2 < Th;
-		const TileSet setB = m->is_complex ? TileSet{stage, Th - stage, Th + stage_im, Th - stage_im} : TileSet{stage, T - stage, 0, 0};
-		const TileSet setB1 = TileSet{stage, stage2 - stage, 0, 0};
-		const TileSet setB2 = m->is_complex ? TileSet{stage2, Th - stage2, Th + stage_im, Th - stage_im} : TileSet{stage2, T - stage2, 0, 0};
-		double* q = ctx->ws.get<double>("pred.q_all", round_up(size_t(count), 128) + size_t(CHUNK_ROWS) * MAX_VAR_SPLITS);
+		// ---- the staged bound: k** - sum Z^2 over a subset of Z's columns is the posterior variance given only those observations,
+		// an upper bound of the variance that is already close to the noise floor inside the point cloud.  The listed rows go
+		// through the tile sets of gate_schedule() one after the other; after each but the last, the queries whose gate the bound
+		// decides (== 1) leave the list.  W is lower triangular, so the columns of the first training blocks are the cheap ones.
+		const int T = n / 128, Th = m->is_complex ? T / 2 : T, Ti = m->is_complex ? Th : 0;
+		const std::vector<GateStage> sched = gate_schedule(ctx, m->is_complex, Th);
+		double* qs = ctx->ws.get<double>("pred.q_all", round_up(size_t(count), 128) + 128);
+		double* qsum = ctx->ws.get<double>("pred.qsum", rows_pad);
+		int* lists[2] = {ctx->ws.get<int>("pred.gate_idx2", round_up(size_t(count), 128)), ctx->ws.get<int>("pred.gate_idx3", round_up(size_t(count), 128))};
+		int* stage_cnt = ctx->ws.get<int>("pred.gate_stage_cnt", MAX_GATE_STAGES);
+		GPLE_CUDA(cudaMemsetAsync(stage_cnt, 0, MAX_GATE_STAGES * sizeof(int), ctx->stream));
 		auto sweep = [&](const int* list, const int list_count, const TileSet& ts, double* qout)
 		{
-			// the triangular products of tile t read K* columns [0, (t + 1) * 128): generate no more than the set needs
+			// the triangular products of tile t read K* columns [0, (t + 1) * 128): generate no more than the set needs, packed at
+			// that pitch, so that a launch of an early stage (few columns) takes up to eight waves of row blocks
 			const int cols = 128 * (1 + std::max(ts.c0 > 0 ? ts.b0 + ts.c0 - 1 : 0, ts.c1 > 0 ? ts.b1 + ts.c1 - 1 : 0));
-			for (long long c0 = 0; c0 < list_count; c0 += CHUNK_ROWS)
+			const long long chunk = (long long)max_rows * std::max(1, std::min(8, n / cols));
+			for (long long c0 = 0; c0 < list_count; c0 += chunk)
 			{
-				const int rows_real = int(std::min<long long>(CHUNK_ROWS, list_count - c0));
+				const int rows_real = int(std::min<long long>(chunk, list_count - c0));
 				const int rows = int(round_up(size_t(rows_real), 128));
 				{
 					ProfScope prof(ctx, GPLE_PROF_KERNEL_BUILD, 8.0 * double(rows) * cols, 1);
-					GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, c0, rows, list, (long long)list_count, Xt2, int(m->N), m->Np, n, cols, m->v, A, nullptr);
+					GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, c0, rows, list, (long long)list_count, Xt2, int(m->N), m->Np, cols, cols, m->v, A, nullptr);
 				}
 				ProfScope prof(ctx, GPLE_PROF_VARIANCE_GEMM, var_gemm_flops(ts, rows), 1);
-				launch_var_gemm(ctx, g_var_variant, A, m->W, n, rows, qout + c0, ts);
+				launch_var_gemm(ctx, g_var_variant, A, cols, m->W, n, rows, qout + c0, ts);
 			}
 		};
-		sweep(gate_idx, count, setA, q);
-		int *slot2 = nullptr, *slot3 = nullptr;
-		double *q2 = nullptr, *q3 = nullptr;
-		if (staged)
+		const int* list = gate_idx;
+		int list_count = count, re0 = 0, im0 = 0;
+		bool first = true;
+		for (size_t s = 0; s <= sched.size() && list_count > 0; s++)
 		{
-			// ---- stage B: only the queries the stage-A bound does not decide see the remaining tiles
-			int* idx2 = ctx->ws.get<int>("pred.gate_idx2", round_up(size_t(count), 128));
-			slot2 = ctx->ws.get<int>("pred.gate_slot2", round_up(size_t(count), 128));
-			int* back2 = split_b ? ctx->ws.get<int>("pred.gate_back2", round_up(size_t(count), 128)) : nullptr;
-			GPLE_LAUNCH(ctx, classify2_kernel, unsigned((count / nb + 255) / 256), 256, 0, pred, gate_idx, q, count / nb, nb, m->prior, idx2, slot2, back2, gate_cnt);
-			GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 204, gate_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-			GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
-			int count2 = 0;
-			std::memcpy(&count2, ctx->h_pinned + 204, sizeof(int));
-			q2 = ctx->ws.get<double>("pred.q2_all", round_up(size_t(count2), 128) + size_t(CHUNK_ROWS) * MAX_VAR_SPLITS);
-			if (!split_b || count2 == 0)
+			const bool last = s == sched.size();
+			const int re1 = last ? Th : sched[s].re_end, im1 = last ? Ti : sched[s].im_end;
+			// the tiles [re0, re1) of the (Re) rows and [Th + im0, Th + im1) of the Im rows, as (up to) two runs
+			const TileSet ts = re1 > re0 ? TileSet{re0, re1 - re0, Th + im0, im1 - im0} : TileSet{Th + im0, im1 - im0, 0, 0};
+			if (last)
 			{
-				ctx->gate_rows_stage_b += (unsigned long long)count2;
-				sweep(idx2, count2, setB, q2);
+				ctx->gate_rows_stage_b += (unsigned long long)list_count; // rows that needed the full variance
 			}
-			else
+			if (ts.count() > 0)
 			{
-				sweep(idx2, count2, setB1, q2);
-				int* idx3 = ctx->ws.get<int>("pred.gate_idx3", round_up(size_t(count2), 128));
-				slot3 = ctx->ws.get<int>("pred.gate_slot3", round_up(size_t(count2), 128));
-				GPLE_LAUNCH(ctx, classify3_kernel, unsigned((count2 / nb + 255) / 256), 256, 0, pred, idx2, back2, q, q2, count2 / nb, nb, m->prior, idx3, slot3, gate_cnt);
-				GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 206, gate_cnt + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-				GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
-				int count3 = 0;
-				std::memcpy(&count3, ctx->h_pinned + 206, sizeof(int));
-				ctx->gate_rows_stage_b += (unsigned long long)count3; // rows that needed the full variance
-				q3 = ctx->ws.get<double>("pred.q3_all", round_up(size_t(count3), 128) + size_t(CHUNK_ROWS) * MAX_VAR_SPLITS);
-				sweep(idx3, count3, setB2, q3);
+				sweep(list, list_count, ts, qs);
+				if (last)
+				{
+					GPLE_LAUNCH(ctx, accumulate_stage_kernel, unsigned((list_count + 255) / 256), 256, 0, list, qs, qsum, int(first), list_count);
+				}
+				else
+				{
+					int* next = lists[s & 1];
+					GPLE_LAUNCH(ctx, classify_stage_kernel, unsigned((list_count / nb + 255) / 256), 256, 0, pred, list, qs, qsum, int(first), list_count / nb, nb, m->prior, next, gate_slot, stage_cnt + s);
+					GPLE_CUDA(cudaMemcpyAsync(ctx->h_pinned + 204, stage_cnt + s, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+					GPLE_CUDA(cudaStreamSynchronize(ctx->stream));
+					std::memcpy(&list_count, ctx->h_pinned + 204, sizeof(int));
+					list = next;
+				}
+				first = false;
 			}
-		}
-		else
-		{
-			ctx->gate_rows_stage_b += (unsigned long long)count;
+			re0 = re1;
+			im0 = im1;
 		}
 		if (m->is_complex)
 		{
-			GPLE_LAUNCH(ctx, finalize_complex_kernel, unsigned((total_rows / 2 + 255) / 256), 256, 0, pred, q, gate_slot, slot2, q2, slot3, q3, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
+			GPLE_LAUNCH(ctx, finalize_complex_kernel, unsigned((total_rows / 2 + 255) / 256), 256, 0, pred, qsum, gate_slot, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
 		}
 		else
 		{
-			GPLE_LAUNCH(ctx, finalize_real_kernel, unsigned((total_rows + 255) / 256), 256, 0, pred, q, gate_slot, slot2, q2, slot3, q3, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
+			GPLE_LAUNCH(ctx, finalize_real_kernel, unsigned((total_rows + 255) / 256), 256, 0, pred, qsum, gate_slot, int(total_rows), 0ll, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
 		}
 		if (d_err != nullptr && d_yq != nullptr)
 		{
@@ -1781,7 +1807,7 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 				GPLE_LAUNCH(ctx, kstar_kernel, (rows + 7) / 8, 256, 0, spec, Xq2, (long long)Q, row0, rows, nullptr, 0ll, Xt2, int(m->N), m->Np, n, n, m->v, A, pred);
 			}
 			ProfScope prof(ctx, GPLE_PROF_VARIANCE_GEMM, double(rows) * n * (double(n) + 128.0), 1);
-			launch_var_gemm(ctx, g_var_variant, A, m->W, n, rows, q, TileSet{0, n / 128, 0, 0});
+			launch_var_gemm(ctx, g_var_variant, A, n, m->W, n, rows, q, TileSet{0, n / 128, 0, 0});
 		}
 		else
 		{
@@ -1792,11 +1818,11 @@ void predict_device(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size
 		}
 		if (m->is_complex)
 		{
-			GPLE_LAUNCH(ctx, finalize_complex_kernel, (rows / 2 + 255) / 256, 256, 0, pred, q, nullptr, nullptr, nullptr, nullptr, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
+			GPLE_LAUNCH(ctx, finalize_complex_kernel, (rows / 2 + 255) / 256, 256, 0, pred, q, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, reinterpret_cast<double2*>(d_pred), d_var, reinterpret_cast<double2*>(d_cut));
 		}
 		else
 		{
-			GPLE_LAUNCH(ctx, finalize_real_kernel, (rows + 255) / 256, 256, 0, pred, q, nullptr, nullptr, nullptr, nullptr, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
+			GPLE_LAUNCH(ctx, finalize_real_kernel, (rows + 255) / 256, 256, 0, pred, q, nullptr, rows, row0, (long long)Q, m->prior, m->rescale, d_pred, d_var, d_cut);
 		}
 		if (d_err != nullptr && d_yq != nullptr)
 		{
@@ -1823,14 +1849,14 @@ double bench_variance_gemm(gple_ctx* ctx, int variant, int rows, int n, int iter
 	double* q = ctx->ws.get<double>("pred.q", size_t(rows) * MAX_VAR_SPLITS);
 	GPLE_CUDA(cudaMemsetAsync(A, 0, size_t(rows) * n * sizeof(double), ctx->stream));
 	GPLE_CUDA(cudaMemsetAsync(W, 0, size_t(n) * n * sizeof(double), ctx->stream));
-	launch_var_gemm(ctx, variant, A, W, n, rows, q, TileSet{0, n / 128, 0, 0});
+	launch_var_gemm(ctx, variant, A, n, W, n, rows, q, TileSet{0, n / 128, 0, 0});
 	cudaEvent_t e0, e1;
 	GPLE_CUDA(cudaEventCreate(&e0));
 	GPLE_CUDA(cudaEventCreate(&e1));
 	GPLE_CUDA(cudaEventRecord(e0, ctx->stream));
 	for (int i = 0; i < iters; i++)
 	{
-		launch_var_gemm(ctx, variant, A, W, n, rows, q, TileSet{0, n / 128, 0, 0});
+		launch_var_gemm(ctx, variant, A, n, W, n, rows, q, TileSet{0, n / 128, 0, 0});
 	}
 	GPLE_CUDA(cudaEventRecord(e1, ctx->stream));
 	GPLE_CUDA(cudaEventSynchronize(e1));

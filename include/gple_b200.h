@@ -70,13 +70,18 @@ extern "C"
 	 *   |f|^2 >= 4 k**                  => gate == 1  (the computed variance k** - sum Z^2 never exceeds the prior k**);
 	 *   |f|^2 <= sigma_f^2 sigma_n^2 / 2 => gate == 0  (var >= sigma_f^2 sigma_n^2 for a query that coincides with no
 	 *                                                   training point; only used while the noise is >= 1e-9 k**).
-	 * The undecided queries then meet a STAGED bound: sum Z^2 over the columns of Z = K* L^-T that belong to the first
-	 * GPLE_OPT_GATE_STAGE_TILES (default -1 = automatic: a quarter of the blocks, between 2 and 8) 128-blocks of training points is the variance explained by those points alone, so
+	 * The undecided queries then meet a STAGED bound: sum Z^2 over the columns of Z = K* L^-T that belong to the first 128-blocks
+	 * of training points is the variance explained by those points alone, so
 	 *   |f|^2 >= 4 (k** - partial sum)  => gate == 1,
-	 * and only the queries this does not decide see the remaining columns (the triangular products of the first blocks are
-	 * the short ones: 4 of 16 blocks cost 1/14 of the flops).  The decided queries get exactly the value the full computation
-	 * gives; the others go through the variance GEMM in a different batch composition (summation order inside the GEMM may
-	 * differ).  GPLE_OPT_GATED_VARIANCE = 0 forces every variance; GPLE_OPT_GATE_STAGE_TILES = 0 disables the staged bound. */
+	 * and only the queries this does not decide see further columns (the triangular products of the first blocks are the short
+	 * ones: block t costs t + 1 tile products).  The schedule is a list of cumulative block boundaries; after each stage but the
+	 * last the decided queries leave the list.  Automatic schedule (GPLE_OPT_GATE_STAGE_TILES = -1, the default): boundaries
+	 * 1, 5, 17, 53, ... up to half of the blocks, then 21/32 of them (complex element: one block of Im rows per five Re blocks
+	 * from the second stage on, then all Re blocks with 3/8 of the Im blocks); gple_ctx_set_gate_schedule sets it explicitly.
+	 * The decided queries get exactly the value the full computation gives; the others go through the variance GEMM in a
+	 * different batch composition (summation order may differ).  GPLE_OPT_GATED_VARIANCE = 0 forces every variance;
+	 * GPLE_OPT_GATE_STAGE_TILES = 0 disables the staged bound; a value t > 0 gives the two boundaries (t, GPLE_OPT_GATE_STAGE2_TILES)
+	 * of the earlier schedule. */
 	enum gple_option
 	{
 		GPLE_OPT_GATED_VARIANCE = 1,
@@ -96,8 +101,13 @@ extern "C"
 		GPLE_OPT_GATE_STAGE2_TILES = 6
 	};
 	int gple_ctx_set_option(gple_ctx* ctx, int option, int value);
-	/* Gated predictions since the last call (then reset): out = {composite rows seen, rows sent through stage A of the
-	 * variance GEMM, rows decided gate == 0 by the noise floor, rows that also needed stage B (the full variance)}. */
+	/* Explicit schedule of the staged bound for the real (complex_element == 0) or the complex element: `stages` cumulative
+	 * boundaries in 128-blocks of training points, re_end[k] blocks of (Re) rows and im_end[k] blocks of Im rows (ignored for the
+	 * real element; may be NULL) seen after stage k; the last stage (everything left) is implied.  Boundaries beyond the model's
+	 * block count are clipped, empty stages dropped.  stages == 0 restores the automatic schedule.  At most 15 stages. */
+	int gple_ctx_set_gate_schedule(gple_ctx* ctx, int complex_element, int stages, const int* re_end, const int* im_end);
+	/* Gated predictions since the last call (then reset): out = {composite rows seen, rows sent through the first stage of the
+	 * variance GEMM, rows decided gate == 0 by the noise floor, rows that reached the last stage (the full variance)}. */
 	int gple_gate_statistics(gple_ctx* ctx, unsigned long long out[4]);
 
 	/* ---- kernel matrices ---------------------------------------------------------------------------

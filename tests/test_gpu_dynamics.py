@@ -128,10 +128,21 @@ def test_bound_gated_variance_changes_nothing(dyn):
     b = dyn.evolve(1, pts, syn.MASS, 1.0, g)
     ctx.set_gated_variance(True)
     ctx.set_gate_stage_tiles(-1)
+    d = dyn.evolve(1, pts, syn.MASS, 1.0, g)  # automatic schedule (several stages)
+    total_d, needed_d, zero_d, last_d = ctx.gate_statistics()
+    # an explicit schedule with ragged boundaries: Im-only stage, boundaries beyond the block count, a repeated boundary
+    ctx.set_gate_schedule(False, [1, 3, 3, 40])
+    ctx.set_gate_schedule(True, [(1, 0), (1, 1), (2, 1), (5, 2), (6, 4), (50, 50)])
+    x = dyn.evolve(1, pts, syn.MASS, 1.0, g)
+    total_x, needed_x, zero_x, last_x = ctx.gate_statistics()
+    ctx.set_gate_schedule(False, [])
+    ctx.set_gate_schedule(True, [])
     for e in range(3):
-        for other in (a, c):
+        for other in (a, c, d, x):
             assert np.array_equal(other[e][:, :2], b[e][:, :2])
             assert np.abs(other[e][:, 2:] - b[e][:, 2:]).max() <= 1e-12 * np.abs(b[e][:, 2:]).max()
     assert total == (8 + 8 + 16) * 5000 and 0 < needed < 0.9 * total and 0 <= zero < total - needed
     assert 0 < stage_b < 0.5 * needed  # the staged bound decides most of the listed rows
     assert (total0, needed0, zero0) == (total, needed, zero) and stage_b0 == needed0  # without stages every listed row is computed in full
+    assert (total_d, needed_d, zero_d) == (total, needed, zero) and (total_x, needed_x, zero_x) == (total, needed, zero)
+    assert 0 < last_d <= stage_b and 0 < last_x <= stage_b  # later boundaries can only decide more queries before the last stage
