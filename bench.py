@@ -325,6 +325,9 @@ def run_ours(args):
     from concurrent.futures import ThreadPoolExecutor
 
     train_ctx = [L.Context(local), L.Context(local), ctx]
+    if args.no_factorise_graphs:
+        for c in train_ctx:
+            c.set_factorise_graphs(False)
     pool = ThreadPoolExecutor(3)
 
     sets, pts_all = make_inputs()
@@ -529,6 +532,7 @@ def main():
     ap.add_argument("--gate-stage-tiles", type=int, default=None, help="override GPLE_OPT_GATE_STAGE_TILES (tuning)")
     ap.add_argument("--gate-stage-tiles-im", type=int, default=-1, help="override GPLE_OPT_GATE_STAGE_TILES_IM (tuning)")
     ap.add_argument("--gate-stage2-tiles", type=int, default=None, help="override GPLE_OPT_GATE_STAGE2_TILES (tuning; 0 = stage B in one part)")
+    ap.add_argument("--no-factorise-graphs", action="store_true", help="GPLE_OPT_FACTORISE_GRAPHS = 0: same kernels launched one by one (for the ncu launch list: ncu does not survive concurrent stream captures from several host threads)")
     ap.add_argument("--gate-schedule-real", default=None, help="explicit schedule of the staged bound, real elements: e.g. 1,5,10 (tuning)")
     ap.add_argument("--gate-schedule-complex", default=None, help="same for the complex element, re:im pairs: e.g. 1:0,5:1,10:2,16:6 (tuning)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2 (default, BASELINE.json configs[1]); c4 = configs[3]: ECR, N=4096, 1e6 evolved points/element, meant for --gpus 8")

@@ -1608,9 +1608,10 @@ constexpr int MAX_GATE_STAGES = 16;
 ///  * gple_ctx_set_gate_schedule: explicit;
 ///  * GPLE_OPT_GATE_STAGE_TILES >= 0: the round-1 / early round-2 schedule (0: single stage; t: [t (+ t/4 Im blocks)], then
 ///    GPLE_OPT_GATE_STAGE2_TILES);
-///  * automatic: Re boundaries 1, 5, 17, 53, ... (b -> 3 b + 2) up to half of the blocks, then 21/32 of them: the first block
-///    alone decides more than half of the open queries for 1/136 of the full product, and each later boundary is placed where the
-///    rows it removes pay for the extra pass (dynamic programme over the measured survival curves, profiles/r02_gate_schedule.md).
+///  * automatic: Re boundaries 1, then a geometric progression (ratio about 2.4) up to 21/32 of the blocks -- 1, 2, 5, 10 of 16;
+///    1, 3, 8, 21 of 32; 1, 2, 6, 14, 35, 84 of 128: the first block alone decides more than half of the open queries for 1/136
+///    of the full product, and each later boundary sits where the rows it removes pay for the extra pass (dynamic programme
+///    over the survival curves of the bench workload, profiles/gate_schedule_sim.py, profiles/r02_gate_schedule.md).
 ///    Complex element: no Im block in the first stage (an Im tile costs a product over ALL Re columns), then one Im block per
 ///    five Re blocks, and a stage with all Re blocks and 3/8 of the Im blocks before the last one.
 std::vector<GateStage> gate_schedule(const gple_ctx* ctx, const bool is_complex, const int Th)
@@ -1637,12 +1638,18 @@ std::vector<GateStage> gate_schedule(const gple_ctx* ctx, const bool is_complex,
 	}
 	else
 	{
-		for (int b = 1; 2 * b <= Th; b = 3 * b + 2)
-		{
-			raw.push_back(GateStage{b, b == 1 ? 0 : std::max(1, b / 5)});
-		}
+		// the first block alone, then boundaries in geometric progression (ratio ~2.4) up to `late` = 21/32 of the blocks
 		const int late = 21 * Th / 32;
-		raw.push_back(GateStage{late, std::max(1, late / 5)});
+		if (late >= 1)
+		{
+			raw.push_back(GateStage{1, 0});
+			const int k = std::max(1, int(std::lround(std::log(double(late)) / std::log(2.4))));
+			for (int i = 1; i <= k; i++)
+			{
+				const int b = std::max(1, int(std::lround(std::pow(double(late), double(i) / k))));
+				raw.push_back(GateStage{b, std::max(1, b / 5)});
+			}
+		}
 		if (is_complex)
 		{
 			raw.push_back(GateStage{Th, std::max(1, 3 * Th / 8)});
