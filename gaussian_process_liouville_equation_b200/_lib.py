@@ -52,6 +52,7 @@ SIGNATURES = {
     "gple_ctx_sync": (C.c_int, [_vp]),
     "gple_ctx_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "gple_ctx_set_gate_schedule": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
+    "gple_gate_schedule_automatic": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int]),
     "gple_gate_statistics": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
     "gple_last_error": (C.c_char_p, [_vp]),
     "gple_launch_count": (C.c_ulonglong, [_vp]),
@@ -249,6 +250,15 @@ def comm_unique_id() -> bytes:
     if rc != OK:
         raise GpleError(rc, "gple_comm_unique_id failed (NCCL not loadable?)")
     return buf.raw
+
+
+def gate_schedule_automatic(complex_element: bool, blocks: int):
+    """The automatic schedule of the staged bound for a model of `blocks` 128-blocks: [(re_end, im_end), ...] (host only)."""
+    re, im = (C.c_int * 16)(), (C.c_int * 16)()
+    n = load().gple_gate_schedule_automatic(int(bool(complex_element)), int(blocks), C.cast(re, C.c_void_p), C.cast(im, C.c_void_p), 16)
+    if n < 0:
+        raise GpleError(-n, "gple_gate_schedule_automatic: bad argument")
+    return [(int(re[k]), int(im[k])) for k in range(min(n, 16))]
 
 
 def partition(total: int, rank: int, nranks: int):

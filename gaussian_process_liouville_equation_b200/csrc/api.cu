@@ -380,6 +380,15 @@ extern "C"
 		return GPLE_OK;
 	}
 
+	int gple_gate_schedule_automatic(int complex_element, int blocks, int* re_end, int* im_end, int capacity)
+	{
+		if (blocks < 0 || capacity < 0 || (capacity > 0 && (re_end == nullptr || im_end == nullptr)))
+		{
+			return -int(GPLE_ERR_ARG);
+		}
+		return gple::gate_schedule_automatic_host(complex_element, blocks, re_end, im_end, capacity);
+	}
+
 	int gple_gate_statistics(gple_ctx* ctx, unsigned long long out[4])
 	{
 		if (ctx == nullptr || out == nullptr)

@@ -1614,6 +1614,47 @@ constexpr int MAX_GATE_STAGES = 16;
 ///    over the survival curves of the bench workload, profiles/gate_schedule_sim.py, profiles/r02_gate_schedule.md).
 ///    Complex element: no Im block in the first stage (an Im tile costs a product over ALL Re columns), then one Im block per
 ///    five Re blocks, and a stage with all Re blocks and 3/8 of the Im blocks before the last one.
+/// cumulative, strictly growing, and something left for the last stage
+std::vector<GateStage> normalise_schedule(const std::vector<GateStage>& raw, const bool is_complex, const int Th)
+{
+	std::vector<GateStage> out;
+	const int Ti = is_complex ? Th : 0;
+	int re = 0, im = 0;
+	for (const GateStage& g : raw)
+	{
+		const int r1 = std::max(re, std::min(g.re_end, Th)), i1 = std::max(im, std::min(g.im_end, Ti));
+		if ((r1 > re || i1 > im) && (r1 < Th || i1 < Ti) && int(out.size()) < MAX_GATE_STAGES - 1)
+		{
+			out.push_back(GateStage{r1, i1});
+			re = r1;
+			im = i1;
+		}
+	}
+	return out;
+}
+
+std::vector<GateStage> automatic_schedule(const bool is_complex, const int Th)
+{
+	std::vector<GateStage> raw;
+	// the first block alone, then boundaries in geometric progression (ratio ~2.4) up to `late` = 21/32 of the blocks
+	const int late = 21 * Th / 32;
+	if (late >= 1)
+	{
+		raw.push_back(GateStage{1, 0});
+		const int k = std::max(1, int(std::lround(std::log(double(late)) / std::log(2.4))));
+		for (int i = 1; i <= k; i++)
+		{
+			const int b = std::max(1, int(std::lround(std::pow(double(late), double(i) / k))));
+			raw.push_back(GateStage{b, std::max(1, b / 5)});
+		}
+	}
+	if (is_complex)
+	{
+		raw.push_back(GateStage{Th, std::max(1, 3 * Th / 8)});
+	}
+	return normalise_schedule(raw, is_complex, Th);
+}
+
 std::vector<GateStage> gate_schedule(const gple_ctx* ctx, const bool is_complex, const int Th)
 {
 	std::vector<GateStage> raw;
@@ -1638,38 +1679,21 @@ std::vector<GateStage> gate_schedule(const gple_ctx* ctx, const bool is_complex,
 	}
 	else
 	{
-		// the first block alone, then boundaries in geometric progression (ratio ~2.4) up to `late` = 21/32 of the blocks
-		const int late = 21 * Th / 32;
-		if (late >= 1)
-		{
-			raw.push_back(GateStage{1, 0});
-			const int k = std::max(1, int(std::lround(std::log(double(late)) / std::log(2.4))));
-			for (int i = 1; i <= k; i++)
-			{
-				const int b = std::max(1, int(std::lround(std::pow(double(late), double(i) / k))));
-				raw.push_back(GateStage{b, std::max(1, b / 5)});
-			}
-		}
-		if (is_complex)
-		{
-			raw.push_back(GateStage{Th, std::max(1, 3 * Th / 8)});
-		}
+		return automatic_schedule(is_complex, Th);
 	}
-	// cumulative, strictly growing, and something left for the last stage
-	std::vector<GateStage> out;
-	const int Ti = is_complex ? Th : 0;
-	int re = 0, im = 0;
-	for (const GateStage& g : raw)
+	return normalise_schedule(raw, is_complex, Th);
+}
+
+/// gple_gate_schedule_automatic of the C-ABI (host only)
+int gate_schedule_automatic_host(const int complex_element, const int blocks, int* re_end, int* im_end, const int capacity)
+{
+	const std::vector<GateStage> s = automatic_schedule(complex_element != 0, blocks);
+	for (size_t k = 0; k < s.size() && int(k) < capacity; k++)
 	{
-		const int r1 = std::max(re, std::min(g.re_end, Th)), i1 = std::max(im, std::min(g.im_end, Ti));
-		if ((r1 > re || i1 > im) && (r1 < Th || i1 < Ti) && int(out.size()) < MAX_GATE_STAGES - 1)
-		{
-			out.push_back(GateStage{r1, i1});
-			re = r1;
-			im = i1;
-		}
+		re_end[k] = s[k].re_end;
+		im_end[k] = s[k].im_end;
 	}
-	return out;
+	return int(s.size());
 }
 
 /// Batched prediction of `Q` points on the device.  d_pred / d_cut hold nb doubles per point.

@@ -24,4 +24,7 @@ void complex_derivatives(gple_ctx* ctx, gple_model* m, unsigned flags, const dou
 void validation_gradient(gple_ctx* ctx, const gple_model* m, const double* d_Xq, size_t Q, const double* d_yq, const double* d_cut, double* h_grad);
 /// NLML / LLT objective (test/gpr.cpp:470-532) of a trained model; grad (nparam doubles, host) may be null
 void nlml_device(gple_ctx* ctx, gple_model* m, double* value, double* grad);
+/// the automatic schedule of the staged bound for a model of `blocks` 128-blocks of training points (host only); returns the number
+/// of stages before the last one and writes at most `capacity` of them
+int gate_schedule_automatic_host(int complex_element, int blocks, int* re_end, int* im_end, int capacity);
 } // namespace gple

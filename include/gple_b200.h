@@ -106,6 +106,10 @@ extern "C"
 	 * real element; may be NULL) seen after stage k; the last stage (everything left) is implied.  Boundaries beyond the model's
 	 * block count are clipped, empty stages dropped.  stages == 0 restores the automatic schedule.  At most 15 stages. */
 	int gple_ctx_set_gate_schedule(gple_ctx* ctx, int complex_element, int stages, const int* re_end, const int* im_end);
+	/* The automatic schedule for an element model of `blocks` 128-blocks of training points (ceil(N / 128)): returns the number of
+	 * stages before the last one (>= 0; negative on a bad argument) and writes the first `capacity` boundaries.  Host only (no
+	 * context, no device): what gple_evolve / gple_predict_* will use unless a schedule or GPLE_OPT_GATE_STAGE_TILES is set. */
+	int gple_gate_schedule_automatic(int complex_element, int blocks, int* re_end, int* im_end, int capacity);
 	/* Gated predictions since the last call (then reset): out = {composite rows seen, rows sent through the first stage of the
 	 * variance GEMM, rows decided gate == 0 by the noise floor, rows that reached the last stage (the full variance)}. */
 	int gple_gate_statistics(gple_ctx* ctx, unsigned long long out[4]);
