@@ -888,6 +888,10 @@ void potrf_trtri(gple_ctx* ctx, double* A, double* W, const int n, int* d_info)
 	{
 		// capture on the context's own stream (the caller's may be the legacy default stream, which cannot capture); relaxed
 		// mode: other host threads of this process keep calling the runtime for their own contexts
+		// One capture at a time per process: it happens once per (size, buffers), and tools that interpose the runtime (ncu) do not
+		// survive simultaneous captures from several host threads.
+		static std::mutex capture_mutex;
+		const std::lock_guard<std::mutex> capture_lock(capture_mutex);
 		const unsigned long long before = ctx->launches;
 		cudaGraph_t graph = nullptr;
 		if (cudaStreamBeginCapture(own, cudaStreamCaptureModeRelaxed) != cudaSuccess)

@@ -65,15 +65,22 @@ using AllPoints = std::array<ElementPoints, NumElements>;	 // lower-triangular o
 
 /// One library context (CUDA stream + workspace) per worker slot.  The C-ABI is thread-safe across contexts, so the
 /// independent element models of a step / of a loss evaluation are built concurrently, each on the context of its slot
-/// (ContextSlot sets the slot of the calling thread).  Slot 0 is the main context.
+/// (ContextSlot sets the slot of the calling thread).  Slot 0 is the main context.  The slots come in GROUPS of three (one per
+/// element): group 0 is the caller's, groups 1 and 2 serve the restart stages that Optimization::optimize runs ahead of time
+/// on threads of their own (ContextGroup).
 class Context
 {
 public:
-	static constexpr int NumSlots = 3;
+	static constexpr int NumGroups = 3, SlotsPerGroup = 3, NumSlots = NumGroups * SlotsPerGroup;
 	static int& slot()
 	{
 		static thread_local int s = 0;
 		return s;
+	}
+	static int& group()
+	{
+		static thread_local int g = 0;
+		return g;
 	}
 	/// RAII: slot 0 for the calling thread within a scope
 	struct ContextSlot0
@@ -91,7 +98,7 @@ public:
 	static gple_ctx* get()
 	{
 		static Context c(device());
-		return c.ctx[slot()];
+		return c.at(slot());
 	}
 	/// Multi-GPU (one process per GPU): gives the main context (slot 0) its NCCL communicator.  Rank 0 draws
 	/// the unique id and publishes it in `id_file` (any path all ranks see: a shared directory of the job); the others
@@ -165,34 +172,74 @@ public:
 	}
 
 private:
-	gple_ctx* ctx[NumSlots] = {nullptr, nullptr, nullptr};
-	explicit Context(int device)
+	gple_ctx* ctx[NumSlots] = {};
+	int dev;
+	std::mutex create_mutex;
+	std::atomic<bool> ready[NumGroups] = {};
+	explicit Context(int device): dev(device) { create_group(0); }
+	/// the three contexts of a slot group come into being when the group is first used
+	void create_group(const int g)
 	{
-		for (auto& c : ctx)
+		const std::lock_guard<std::mutex> lock(create_mutex);
+		if (ready[g].load(std::memory_order_acquire))
 		{
-			if (gple_ctx_create(device, &c) != GPLE_OK)
+			return;
+		}
+		for (int k = 0; k < SlotsPerGroup; k++)
+		{
+			if (gple_ctx_create(dev, &ctx[g * SlotsPerGroup + k]) != GPLE_OK)
 			{
 				throw std::runtime_error("gple_ctx_create failed: no CUDA device (there is no CPU fallback)");
 			}
 		}
+		ready[g].store(true, std::memory_order_release);
+	}
+	gple_ctx* at(const int s)
+	{
+		const int g = s / SlotsPerGroup;
+		if (!ready[g].load(std::memory_order_acquire))
+		{
+			create_group(g);
+		}
+		return ctx[s];
 	}
 	~Context()
 	{
 		for (auto& c : ctx)
 		{
-			gple_ctx_destroy(c);
+			if (c != nullptr)
+			{
+				gple_ctx_destroy(c);
+			}
 		}
 	}
 };
 
-/// RAII: the calling thread uses the context of slot k until the guard goes out of scope
+/// RAII: the calling thread uses the context of slot k OF ITS GROUP until the guard goes out of scope
 struct ContextSlot
 {
 	int previous;
-	explicit ContextSlot(const int k): previous(Context::slot()) { Context::slot() = k % Context::NumSlots; }
+	explicit ContextSlot(const int k): previous(Context::slot()) { Context::slot() = Context::group() * Context::SlotsPerGroup + k % Context::SlotsPerGroup; }
 	~ContextSlot() { Context::slot() = previous; }
 	ContextSlot(const ContextSlot&) = delete;
 	ContextSlot& operator=(const ContextSlot&) = delete;
+};
+/// RAII: the calling thread works in slot group g (its own three contexts, element workers and model-cache entries)
+struct ContextGroup
+{
+	int previous_group, previous_slot;
+	explicit ContextGroup(const int g): previous_group(Context::group()), previous_slot(Context::slot())
+	{
+		Context::group() = g % Context::NumGroups;
+		Context::slot() = Context::group() * Context::SlotsPerGroup;
+	}
+	~ContextGroup()
+	{
+		Context::group() = previous_group;
+		Context::slot() = previous_slot;
+	}
+	ContextGroup(const ContextGroup&) = delete;
+	ContextGroup& operator=(const ContextGroup&) = delete;
 };
 
 /// Multi-GPU: the element models are independent, so with G ranks element e is trained / optimised on ONE
@@ -212,16 +259,24 @@ inline void all_reduce_sum(std::vector<double>& v)
 	}
 }
 
-/// Two persistent worker threads, bound to the context slots 1 and 2 (slot 0 is the calling thread).  An optimisation makes
-/// thousands of three-element evaluations of a millisecond or less each: spawning threads per evaluation would cost as much as
-/// the evaluation itself.
+/// Two persistent worker threads per slot group, bound to the group's context slots 1 and 2 (slot 0 is the calling thread).  An
+/// optimisation makes thousands of three-element evaluations of a millisecond or less each: spawning threads per evaluation
+/// would cost as much as the evaluation itself.
 class ElementWorkers
 {
 public:
+	/// the workers of the calling thread's group (created on first use)
 	static ElementWorkers& instance()
 	{
-		static ElementWorkers w;
-		return w;
+		static std::mutex m;
+		static std::array<std::unique_ptr<ElementWorkers>, Context::NumGroups> w;
+		const int g = Context::group();
+		const std::lock_guard<std::mutex> lock(m);
+		if (!w[g])
+		{
+			w[g].reset(new ElementWorkers(g));
+		}
+		return *w[g];
 	}
 	static bool& inside_worker()
 	{
@@ -262,14 +317,15 @@ private:
 		std::thread th;
 	};
 	std::array<Worker, 2> Workers;
-	ElementWorkers()
+	explicit ElementWorkers(const int group)
 	{
 		for (int k = 1; k <= 2; k++)
 		{
 			Worker& w = Workers[k - 1];
 			w.th = std::thread(
-				[&w, k]()
+				[&w, k, group]()
 				{
+					const ContextGroup in_group(group);
 					const ContextSlot guard(k);
 					inside_worker() = true;
 					std::unique_lock<std::mutex> lock(w.m);
@@ -300,6 +356,8 @@ private:
 			);
 		}
 	}
+
+public:
 	~ElementWorkers()
 	{
 		for (Worker& w : Workers)
@@ -736,6 +794,7 @@ private:
 	struct Entry
 	{
 		const ElementTrainingSet* key;
+		int group; // slot group of the thread that built it: concurrent restart stages keep one entry per training set EACH
 		std::uint64_t print;
 		ParameterVector theta;
 		unsigned flags;
@@ -751,11 +810,12 @@ private:
 	{
 		const unsigned want = (err ? 1u : 0u) | (avg ? 2u : 0u) | (deriv ? 4u : 0u);
 		const std::uint64_t print = fingerprint(ts);
+		const int group = Context::group();
 		{
 			const std::lock_guard<std::mutex> lock(Mutex);
 			for (const auto& e : entries)
 			{
-				if (e.key == &ts && e.print == print && e.theta == theta && (e.flags & want) == want)
+				if (e.key == &ts && e.group == group && e.print == print && e.theta == theta && (e.flags & want) == want)
 				{
 					Hits++;
 					return e.model;
@@ -763,18 +823,18 @@ private:
 			}
 		}
 		Misses++;
-		// the same element is never evaluated by two threads at once, so training happens outside the lock
+		// within a slot group the same element is never evaluated by two threads at once, so training happens outside the lock
 		auto model = std::make_shared<const K>(theta, ts, err, avg, deriv);
 		const std::lock_guard<std::mutex> lock(Mutex);
 		for (auto& e : entries)
 		{
-			if (e.key == &ts)
+			if (e.key == &ts && e.group == group)
 			{
-				e = Entry<K>{&ts, print, theta, want, model};
+				e = Entry<K>{&ts, group, print, theta, want, model};
 				return model;
 			}
 		}
-		entries.push_back(Entry<K>{&ts, print, theta, want, model});
+		entries.push_back(Entry<K>{&ts, group, print, theta, want, model});
 		return model;
 	}
 };

@@ -387,6 +387,15 @@ public:
 	AllParameters get_lower_bounds() const { return {LocalMinimizers[0].get_lower_bounds(), LocalMinimizers[1].get_lower_bounds(), LocalMinimizers[2].get_lower_bounds()}; }
 	AllParameters get_upper_bounds() const { return {LocalMinimizers[0].get_upper_bounds(), LocalMinimizers[1].get_upper_bounds(), LocalMinimizers[2].get_upper_bounds()}; }
 
+	/// Restart stages ahead of time (default on; single-GPU runs only).  optimize() tries up to three starts one after the other
+	/// (opt.cpp:1320-1383): the previous parameters, the initial parameters, a global search -- each a full local sequence of
+	/// thousands of millisecond-sized, latency-bound evaluations that leave most of the GPU idle, and the later ones only run when
+	/// the earlier result misses the averages.  With this option stages 2 and 3 start at once on threads and contexts of their own
+	/// (slot groups 1 and 2) next to stage 1; the acceptance rules are then applied in the reference's order to the finished
+	/// results, and a stage whose result turns out not to be needed is stopped at its next iteration and discarded.  Evaluations are
+	/// deterministic, so the outcome (parameters, error, evaluation counts, result type) is the sequential one.
+	void set_speculative_restarts(const bool on) { SpeculativeRestarts = on; }
+
 	/// gple/opt.cpp:1019-1392
 	Result optimize(const AllPoints& density, const AllPoints& extra_points)
 	{
@@ -415,68 +424,7 @@ public:
 			}
 		}
 		set_optimizer_bounds(ParameterBounds);
-		const bool OffDiagonalPopulated = !density[1].empty();
-		auto move_into_bounds = [&ParameterBounds](AllParameters& pv)
-		{
-			for (std::size_t e = 0; e < NumElements; e++)
-			{
-				for (std::size_t p = 0; p < pv[e].size(); p++)
-				{
-					pv[e][p] = std::clamp(pv[e][p], ParameterBounds[e][0][p], ParameterBounds[e][1][p]);
-				}
-			}
-		};
-		// opt.cpp:1101-1198
-		auto do_optimize = [&](AllParameters& pv, const OptimizationType type) -> Result
-		{
-			for (auto& p : pv)
-			{
-				p[0] = InitialMagnitude;
-			}
-			move_into_bounds(pv);
-			auto [err, steps] = optimize_elementwise(TrainingSets, ExtraTrainingSets, LocalMinimizers, pv, false);
-			if (OffDiagonalPopulated)
-			{
-				const auto [derr, dsteps] = optimize_diagonal(TrainingSets, ExtraTrainingSets, Energies, pv, false);
-				(void)derr;
-				const auto [ferr, fsteps] = optimize_full(TrainingSets, ExtraTrainingSets, Energies, pv);
-				err = ferr;
-				steps.push_back(dsteps);
-				steps.push_back(fsteps);
-			}
-			else
-			{
-				const auto [derr, dsteps] = optimize_diagonal(TrainingSets, ExtraTrainingSets, Energies, pv, true);
-				err = derr;
-				steps.push_back(dsteps);
-				steps.push_back(0);
-			}
-			// opt.cpp:1179-1195: the magnitude follows from the optimised kernel
-			const TrainingKernels k(pv, TrainingSets, false, false, false);
-			for (std::size_t i = 0; i < NumPES; i++)
-			{
-				if (k.Diagonal[i])
-				{
-					pv[2 * i][0] = k.Diagonal[i]->get_magnitude();
-				}
-			}
-			if (k.OffDiagonal)
-			{
-				pv[1][0] = k.OffDiagonal->get_magnitude();
-			}
-			return {err, steps, type};
-		};
-		// opt.cpp:1200-1270: relative deviations of the averages, 0 when within tolerance
-		auto check_averages = [&](const AllParameters& pv) -> std::array<double, 3>
-		{
-			const TrainingKernels k(pv, TrainingSets, false, true, false);
-			auto beyond = [](const double calc, const double ref)
-			{
-				const double err = std::abs(calc / ref - 1.0);
-				return err < AverageTolerance ? 0.0 : err;
-			};
-			return {beyond(k.calculate_population(), 1.0), beyond(k.calculate_total_energy_average(Energies), TotalEnergy), beyond(k.calculate_purity(), Purity)};
-		};
+		const StageInputs in{TrainingSets, ExtraTrainingSets, Energies, ParameterBounds, !density[1].empty()};
 		auto any = [](const std::array<double, 3>& c) { return c[0] != 0.0 || c[1] != 0.0 || c[2] != 0.0; };
 		// opt.cpp:1272-1318
 		auto compare_and_overwrite = [this](Result& result, std::array<double, 3>& check, const Result& result_new, const std::array<double, 3>& check_new, const AllParameters& pv_new)
@@ -502,19 +450,78 @@ public:
 				check = check_new;
 			}
 		};
+		// stages 2 and 3 ahead of time: a copy of this optimiser (same bounds, tolerances, targets) per stage, on its own slot group
+		const bool speculate = SpeculativeRestarts && Context::num_ranks() == 1 && Context::group() == 0;
+		struct Speculation
+		{
+			std::unique_ptr<Optimization> worker;
+			std::atomic<bool> stop{false};
+			std::thread th;
+			StageOutcome out;
+			std::exception_ptr error;
+			void finish()
+			{
+				if (th.joinable())
+				{
+					th.join();
+				}
+			}
+			void cancel()
+			{
+				stop.store(true);
+				finish();
+			}
+			~Speculation() { cancel(); }
+		};
+		std::array<Speculation, 2> ahead; // destroyed (stopped and joined) before the cache guard and the training sets
+		if (speculate)
+		{
+			for (int k = 0; k < 2; k++)
+			{
+				Speculation& sp = ahead[k];
+				sp.worker.reset(new Optimization(*this));
+				sp.worker->set_stop_flag(&sp.stop);
+				sp.th = std::thread(
+					[&sp, &in, k]()
+					{
+						const ContextGroup group(k + 1);
+						try
+						{
+							sp.out = k == 0 ? sp.worker->stage_from_initial(in) : sp.worker->stage_from_global(in);
+						}
+						catch (...)
+						{
+							sp.error = std::current_exception();
+						}
+					}
+				);
+			}
+		}
+		auto stage = [&](const int k) -> StageOutcome
+		{
+			if (!speculate)
+			{
+				return k == 0 ? stage_from_initial(in) : stage_from_global(in);
+			}
+			ahead[k].finish();
+			if (ahead[k].error)
+			{
+				std::rethrow_exception(ahead[k].error);
+			}
+			return ahead[k].out;
+		};
 
 		// 1. from the previous parameters (opt.cpp:1320-1333)
-		Result result = do_optimize(ParameterVectors, LocalPrevious);
-		std::array<double, 3> check = check_averages(ParameterVectors);
+		Result result = do_optimize(in, ParameterVectors, LocalPrevious);
+		std::array<double, 3> check = check_averages(in, ParameterVectors);
 		if (!any(check))
 		{
 			return result;
 		}
 		// 2. from the initial parameters (opt.cpp:1335-1352)
 		{
-			AllParameters pv{InitialKernelParameter, InitialComplexKernelParameter, InitialKernelParameter};
-			const Result r2 = do_optimize(pv, LocalInitial);
-			compare_and_overwrite(result, check, r2, check_averages(pv), pv);
+			const StageOutcome s2 = stage(0);
+			compare_and_overwrite(result, check, s2.result, s2.check, s2.pv);
 			if (!any(check))
 			{
 				return result;
@@ -522,22 +529,126 @@ public:
 		}
 		// 3. global search per element in log space, then the local sequence from there (opt.cpp:1354-1383)
 		{
-			AllParameters pv{InitialKernelParameter, InitialComplexKernelParameter, InitialKernelParameter};
-			move_into_bounds(pv);
-			const auto [gerr, gsteps] = optimize_elementwise(TrainingSets, ExtraTrainingSets, GlobalMinimizers, pv, true);
-			(void)gerr;
-			Result r3 = do_optimize(pv, Global);
-			auto& steps = std::get<1>(r3);
-			for (std::size_t i = 0; i < gsteps.size() && i < steps.size(); i++)
-			{
-				steps[i] += gsteps[i];
-			}
-			compare_and_overwrite(result, check, r3, check_averages(pv), pv);
+			const StageOutcome s3 = stage(1);
+			compare_and_overwrite(result, check, s3.result, s3.check, s3.pv);
 		}
 		return result;
 	}
 
 private:
+	/// what every restart stage of one optimize() call works from
+	struct StageInputs
+	{
+		const AllTrainingSets& TrainingSets;
+		const AllTrainingSets& ExtraTrainingSets;
+		const QuantumVectorD& Energies;
+		const std::array<Bounds, NumElements>& ParameterBounds;
+		bool OffDiagonalPopulated;
+	};
+	struct StageOutcome
+	{
+		AllParameters pv;
+		Result result;
+		std::array<double, 3> check{0.0, 0.0, 0.0};
+	};
+	bool SpeculativeRestarts = true;
+	void set_stop_flag(const std::atomic<bool>* flag)
+	{
+		for (std::size_t e = 0; e < NumElements; e++)
+		{
+			LocalMinimizers[e].set_stop_flag(flag);
+			GlobalMinimizers[e].set_stop_flag(flag);
+		}
+		DiagonalMinimizer.set_stop_flag(flag);
+		FullMinimizer.set_stop_flag(flag);
+	}
+	static void move_into_bounds(const StageInputs& in, AllParameters& pv)
+	{
+		for (std::size_t e = 0; e < NumElements; e++)
+		{
+			for (std::size_t p = 0; p < pv[e].size(); p++)
+			{
+				pv[e][p] = std::clamp(pv[e][p], in.ParameterBounds[e][0][p], in.ParameterBounds[e][1][p]);
+			}
+		}
+	}
+	/// opt.cpp:1101-1198: the local sequence (per element, diagonal with constraints, all elements with constraints) from pv
+	Result do_optimize(const StageInputs& in, AllParameters& pv, const OptimizationType type)
+	{
+		for (auto& p : pv)
+		{
+			p[0] = InitialMagnitude;
+		}
+		move_into_bounds(in, pv);
+		auto [err, steps] = optimize_elementwise(in.TrainingSets, in.ExtraTrainingSets, LocalMinimizers, pv, false);
+		if (in.OffDiagonalPopulated)
+		{
+			const auto [derr, dsteps] = optimize_diagonal(in.TrainingSets, in.ExtraTrainingSets, in.Energies, pv, false);
+			(void)derr;
+			const auto [ferr, fsteps] = optimize_full(in.TrainingSets, in.ExtraTrainingSets, in.Energies, pv);
+			err = ferr;
+			steps.push_back(dsteps);
+			steps.push_back(fsteps);
+		}
+		else
+		{
+			const auto [derr, dsteps] = optimize_diagonal(in.TrainingSets, in.ExtraTrainingSets, in.Energies, pv, true);
+			err = derr;
+			steps.push_back(dsteps);
+			steps.push_back(0);
+		}
+		// opt.cpp:1179-1195: the magnitude follows from the optimised kernel
+		const TrainingKernels k(pv, in.TrainingSets, false, false, false);
+		for (std::size_t i = 0; i < NumPES; i++)
+		{
+			if (k.Diagonal[i])
+			{
+				pv[2 * i][0] = k.Diagonal[i]->get_magnitude();
+			}
+		}
+		if (k.OffDiagonal)
+		{
+			pv[1][0] = k.OffDiagonal->get_magnitude();
+		}
+		return {err, steps, type};
+	}
+	/// opt.cpp:1200-1270: relative deviations of the averages, 0 when within tolerance
+	std::array<double, 3> check_averages(const StageInputs& in, const AllParameters& pv) const
+	{
+		const TrainingKernels k(pv, in.TrainingSets, false, true, false);
+		auto beyond = [](const double calc, const double ref)
+		{
+			const double err = std::abs(calc / ref - 1.0);
+			return err < AverageTolerance ? 0.0 : err;
+		};
+		return {beyond(k.calculate_population(), 1.0), beyond(k.calculate_total_energy_average(in.Energies), TotalEnergy), beyond(k.calculate_purity(), Purity)};
+	}
+	/// stage 2 (opt.cpp:1335-1352): the local sequence from the initial parameters
+	StageOutcome stage_from_initial(const StageInputs& in)
+	{
+		StageOutcome o;
+		o.pv = AllParameters{InitialKernelParameter, InitialComplexKernelParameter, InitialKernelParameter};
+		o.result = do_optimize(in, o.pv, LocalInitial);
+		o.check = check_averages(in, o.pv);
+		return o;
+	}
+	/// stage 3 (opt.cpp:1354-1383): global search per element in log space, then the local sequence from there
+	StageOutcome stage_from_global(const StageInputs& in)
+	{
+		StageOutcome o;
+		o.pv = AllParameters{InitialKernelParameter, InitialComplexKernelParameter, InitialKernelParameter};
+		move_into_bounds(in, o.pv);
+		const auto [gerr, gsteps] = optimize_elementwise(in.TrainingSets, in.ExtraTrainingSets, GlobalMinimizers, o.pv, true);
+		(void)gerr;
+		o.result = do_optimize(in, o.pv, Global);
+		auto& steps = std::get<1>(o.result);
+		for (std::size_t i = 0; i < gsteps.size() && i < steps.size(); i++)
+		{
+			steps[i] += gsteps[i];
+		}
+		o.check = check_averages(in, o.pv);
+		return o;
+	}
 	static constexpr int MaximumGlobalEvaluations = 100000;		// opt.cpp:339
 	static constexpr int MaximumConstrainedEvaluations = 2000;	// none in the reference (see set_maximum_evaluations)
 	const double TotalEnergy;

@@ -17,6 +17,7 @@
 // No GPU dependency: tests/cpp/nlopt_lite_test.cpp exercises this header on analytic problems.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstddef>
 #include <limits>
@@ -93,6 +94,16 @@ public:
 	void set_maxeval(const int n) { MaxEval = n; }
 	void set_initial_step(const double s) { InitialStep = s; }
 	void set_local_optimizer(const opt& local) { LocalStore.assign(1, local); }
+	/// nlopt::opt::force_stop, as a flag the caller owns: once it reads true the running optimisation stops at its next
+	/// iteration (the result is then whatever was reached; a caller that raises the flag discards it)
+	void set_stop_flag(const std::atomic<bool>* flag)
+	{
+		StopFlag = flag;
+		for (opt& l : LocalStore)
+		{
+			l.set_stop_flag(flag);
+		}
+	}
 	int get_numevals() const { return NumEvals; }
 
 	/// Minimise from x (in place); returns the reason for stopping, the minimum in opt_f.
@@ -176,7 +187,8 @@ private:
 
 	static constexpr double FeasibilityFloor = 1e-6;
 	static const std::vector<double>& checked(const std::vector<double>& v) { return v; }
-	bool budget_left() const { return MaxEval <= 0 || NumEvals < MaxEval; }
+	const std::atomic<bool>* StopFlag = nullptr;
+	bool budget_left() const { return (MaxEval <= 0 || NumEvals < MaxEval) && !(StopFlag != nullptr && StopFlag->load(std::memory_order_relaxed)); }
 
 	/// objective in the reduced coordinates
 	double value(const std::vector<double>& z, std::vector<double>* grad = nullptr)
@@ -625,7 +637,7 @@ private:
 		const int maxeval = MaxEval > 0 ? MaxEval : 2000;
 		result r = MAXEVAL_REACHED;
 		int stall = 0;
-		while (NumEvals < maxeval)
+		while (NumEvals < maxeval && budget_left())
 		{
 			// best rectangle of every size class (size = longest side = 3^-minlevel)
 			int maxl = 0;

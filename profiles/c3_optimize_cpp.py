@@ -14,8 +14,8 @@ from test_opt_cpp import run_cpp
 SIZES = [int(a) for a in sys.argv[1:]] or [300, 1024]
 DAC = 1
 print("# C3: full Optimization::optimize() through the C++ host on 1 x B200 (DAC, three elements, M = 5N extra points per element)\n")
-print("| N | wall s | evaluations (NM x3, diagonal, full) | evaluations / s | result type | final loss | population | energy / E0 | purity |")
-print("|---:|---:|---|---:|---|---:|---:|---:|---:|")
+print("| N | restart stages | wall s | evaluations (NM x3, diagonal, full) | evaluations / s | result type | final loss | population | energy / E0 | purity |")
+print("|---:|---|---:|---|---:|---|---:|---:|---:|---:|")
 for N in SIZES:
     centre = (0.0, syn.P0)
     density, extra = [], []
@@ -27,7 +27,9 @@ for N in SIZES:
     pops = [dynamics.observable_sums(DAC, density[e], syn.MASS, i) for i, e in enumerate((0, 2))]
     e_tot = 0.6 * pops[0][7] / pops[0][0] + 0.4 * pops[1][7] / pops[1][0]
     purity0 = syn.snapshot_purity()
-    with tempfile.TemporaryDirectory() as tmp:
-        got = run_cpp(density, extra, DAC, e_tot, purity0, tmp, 300, 2000)
-    steps = [int(got[f"steps{i}"]) for i in range(5)]
-    print(f"| {N} | {got['wall_s']:.2f} | {steps} | {got['evaluations'] / got['wall_s']:.1f} | {int(got['type'])} | {got['error']:.4g} | {got['population']:.4f} | {got['energy'] / e_tot:.4f} | {got['purity']:.4f} |", flush=True)
+    for mode in ("1", "0"):  # Optimization::set_speculative_restarts: stages 2 and 3 ahead of time / one after the other
+        os.environ["GPLE_SPECULATIVE_RESTARTS"] = mode
+        with tempfile.TemporaryDirectory() as tmp:
+            got = run_cpp(density, extra, DAC, e_tot, purity0, tmp, 300, 2000)
+        steps = [int(got[f"steps{i}"]) for i in range(5)]
+        print(f"| {N} | {'concurrent' if mode == '1' else 'sequential'} | {got['wall_s']:.2f} | {steps} | {got['evaluations'] / got['wall_s']:.1f} | {int(got['type'])} | {got['error']:.4g} | {got['population']:.4f} | {got['energy'] / e_tot:.4f} | {got['purity']:.4f} |", flush=True)

@@ -5,6 +5,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 
 using namespace gple_host;
@@ -41,6 +42,10 @@ int main(int argc, char** argv)
 	const double sp = 0.7056, sx = 1.0 / (2.0 * sp);
 	Optimization optimizer({sx, sp}, {20.0, 40.0}, mass, pes_model, e0, purity);
 	optimizer.set_maximum_evaluations(argc > 6 ? std::atoi(argv[6]) : 200, argc > 7 ? std::atoi(argv[7]) : 1000);
+	if (const char* spec = std::getenv("GPLE_SPECULATIVE_RESTARTS")) // "0": the restart stages one after the other
+	{
+		optimizer.set_speculative_restarts(std::atoi(spec) != 0);
+	}
 	const auto t0 = std::chrono::steady_clock::now();
 	const auto [err, steps, type] = optimizer.optimize(density, extra);
 	const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -148,6 +148,37 @@ def test_cpp_optimiser_three_elements_logic(tmp_path):
     assert got["steps0"] > 0 and got["steps1"] > 0 and got["steps2"] > 0 and got["steps3"] > 0 and got["steps4"] > 0
 
 
+def test_speculative_restart_stages_change_nothing(tmp_path):
+    """Optimization::set_speculative_restarts: stages 2 and 3 of optimize() run ahead of time on their own threads, contexts and
+    copies of the minimisers; the outcome -- every parameter, the error, the result type, the evaluation counts -- is the one of the
+    sequential run, whichever stage is finally kept."""
+    from test_opt_cpp import write_points
+
+    exe = compile_on_mock(os.path.join(ROOT, "tests", "cpp", "opt_test.cpp"), "opt_test")
+    n, centre = 16, (0.0, syn.P0)
+    density, extra = [], []
+    for e in range(3):
+        X, y = syn.training_set(63, e, n, centre)
+        Xe, ye = syn.extra_points(63, e, X, 5 * n, centre)
+        density.append(syn.points_aos(X, y))
+        extra.append(syn.points_aos(Xe, ye))
+    o = [oracle_backend.observable_sums(1, density[e], syn.MASS, i) for i, e in enumerate((0, 2))]
+    e0 = 0.6 * o[0][7] / o[0][0] + 0.4 * o[1][7] / o[1][0]
+    path = os.path.join(tmp_path, "points.txt")
+    write_points(path, density, extra)
+    types = set()
+    # an unreachable purity target makes every stage miss the averages (all three are needed); the true one may stop earlier
+    for purity in (syn.snapshot_purity(), 3.0):
+        runs = []
+        for spec in ("1", "0"):
+            env = dict(os.environ, GPLE_SPECULATIVE_RESTARTS=spec)
+            out = subprocess.run([exe, path, "1", repr(syn.MASS), repr(e0), repr(purity), "40", "80"], capture_output=True, text=True, check=True, timeout=900, env=env).stdout
+            runs.append({k: v for k, v in (line.split() for line in out.strip().splitlines()) if k != "wall_s"})
+        assert runs[0] == runs[1]  # text-identical: bitwise equal doubles at 17 digits
+        types.add(int(runs[0]["type"]))
+    assert 3 in types  # the global stage was reached (and kept) at least once
+
+
 def test_main_loop_logic_at_the_crossing():
     """Started at the crossing the run must populate rho10 and rho11: is_very_small, new_element_point_selection (Metropolis
     tuning on the new_point_predict target, extra points) and the element-change re-optimisation of main.cpp:145-162."""

@@ -107,6 +107,30 @@ def test_cpp_optimiser_three_elements(tmp_path):
 
 
 @pytest.mark.gpu
+def test_speculative_restart_stages_change_nothing_on_the_gpu(tmp_path, monkeypatch):
+    """Optimization::set_speculative_restarts on the real library: three restart stages on nine contexts at once against the same
+    stages one after the other -- identical parameters, error, result type and evaluation counts (the library's results do not
+    depend on what else runs on the device)."""
+    n, centre = 96, (0.0, syn.P0)
+    density, extra = [], []
+    for e in range(3):
+        X, y = syn.training_set(63, e, n, centre)
+        Xe, ye = syn.extra_points(63, e, X, 5 * n, centre)
+        density.append(syn.points_aos(X, y))
+        extra.append(syn.points_aos(Xe, ye))
+    import oracle_backend
+
+    o = [oracle_backend.observable_sums(1, density[e], syn.MASS, i) for i, e in enumerate((0, 2))]
+    e0 = 0.6 * o[0][7] / o[0][0] + 0.4 * o[1][7] / o[1][0]
+    runs = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GPLE_SPECULATIVE_RESTARTS", mode)
+        got = run_cpp(density, extra, 1, e0, 3.0, str(tmp_path), 100, 300)  # purity 3 is unreachable: every stage is needed
+        runs.append({k: v for k, v in got.items() if k != "wall_s"})
+    assert runs[0] == runs[1] and runs[0]["evaluations"] > 500
+
+
+@pytest.mark.gpu
 def test_cpp_optimiser_outcome_at_n300_is_verified_by_the_oracle_and_locally_optimal(tmp_path):
     """C3-shaped run (DAC, three populated elements, N = 300, M = 5 N) through the C++ host on the GPU, checked three ways
     (the 20 % asserts of the small test say nothing):
