@@ -483,7 +483,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "var_gemm_kernel (Z = K* W^T, fused row sum of squares; FP64 DMMA)", "achieved": achieved,
                      "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak if dmma_peak > 0 else None, "traffic": 2.338e9 * (var_flops / max(var_n, 1)) / 8.442e10,
-                     "traffic_note": "ncu dram__bytes_read+write of a real-element launch (2.338 GB for 8.44e10 flops, profiles/r01_var_gemm_ncu_full.md), scaled by flops per launch",
+                     "traffic_note": "ncu dram__bytes_read+write of a real-element launch (2.338 GB for 8.44e10 flops, profiles/r01_var_gemm_ncu_full.md), scaled by flops per launch; the launches of the multi-stage schedule measure 0.028-0.031 bytes per flop, early and late stages alike (profiles/r02_ncu_summary.md, addendum)",
                      "peak_source": "measured live by gple_measure_fp64_peak (register-resident DMMA.8x8x4 loop); MEASURED_PEAKS.json has no FP64 entry",
                      "launches": var_n, "avg_launch_ms": var_ms / max(var_n, 1), "share_of_step": var_ms / total_ms,
                      "flops_counted": "executed flops of every launch: 2*128^2*sum over its n-tile set of (tile+1) per row (= rows*n*(n+128) for the full triangular product; the reference formulation K* K^-1 k^T would be 2x that)"},
