@@ -76,8 +76,9 @@ extern "C"
 	 * and only the queries this does not decide see further columns (the triangular products of the first blocks are the short
 	 * ones: block t costs t + 1 tile products).  The schedule is a list of cumulative block boundaries; after each stage but the
 	 * last the decided queries leave the list.  Automatic schedule (GPLE_OPT_GATE_STAGE_TILES = -1, the default): boundaries
-	 * 1, 5, 17, 53, ... up to half of the blocks, then 21/32 of them (complex element: one block of Im rows per five Re blocks
-	 * from the second stage on, then all Re blocks with 3/8 of the Im blocks); gple_ctx_set_gate_schedule sets it explicitly.
+	 * 1, then a geometric progression (ratio about 2.4) up to 21/32 of the blocks -- 1, 2, 5, 10 of 16 blocks; 1, 2, 6, 14, 35, 84 of
+	 * 128 (complex element: no Im block in the first stage, one block of Im rows per five Re blocks afterwards, then all Re blocks
+	 * with 3/8 of the Im blocks); gple_gate_schedule_automatic returns it, gple_ctx_set_gate_schedule replaces it.
 	 * The decided queries get exactly the value the full computation gives; the others go through the variance GEMM in a
 	 * different batch composition (summation order may differ).  GPLE_OPT_GATED_VARIANCE = 0 forces every variance;
 	 * GPLE_OPT_GATE_STAGE_TILES = 0 disables the staged bound; a value t > 0 gives the two boundaries (t, GPLE_OPT_GATE_STAGE2_TILES)
@@ -86,7 +87,7 @@ extern "C"
 	{
 		GPLE_OPT_GATED_VARIANCE = 1,
 		GPLE_OPT_GATE_STAGE_TILES = 2,
-		GPLE_OPT_GATE_STAGE_TILES_IM = 3, /* complex element: blocks of Im rows in the stage (default -1 = a quarter of the Re blocks, at least 1) */
+		GPLE_OPT_GATE_STAGE_TILES_IM = 3, /* with GPLE_OPT_GATE_STAGE_TILES = t > 0, complex element: blocks of Im rows in the stage (default -1 = a quarter of the Re blocks, at least 1) */
 		/* (default 1) one step of iterative refinement of v = K^-1 y' after the factorisation (residual against the regenerated
 		 * covariance): v at the accuracy of the reference's LDLT solve (kernel.cpp:281-284) instead of that of the explicit
 		 * triangular inverse; 0 only for measuring the difference (tests/test_gpu_baseline_sizes.py) */
@@ -95,7 +96,7 @@ extern "C"
 		 * n = 2048) is captured once per (size, buffers) into a CUDA graph and replayed: the launch-bound inner loop of every model
 		 * rebuild and of every loss evaluation of the optimiser.  Same kernels, same results; 0 for measuring the difference. */
 		GPLE_OPT_FACTORISE_GRAPHS = 5,
-		/* staged gate, second boundary (default -1 = five eighths of the training blocks): the queries the stage-A bound leaves open
+		/* with GPLE_OPT_GATE_STAGE_TILES = t > 0: second boundary (default -1 = five eighths of the training blocks): the queries the stage-A bound leaves open
 		 * first see the blocks [stage, stage2) only; the tighter bound decides another fifth of them before the long products of
 		 * the last blocks.  A value <= the stage runs the rest in one part (round-1 schedule). */
 		GPLE_OPT_GATE_STAGE2_TILES = 6
