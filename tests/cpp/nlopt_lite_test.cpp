@@ -1,6 +1,7 @@
 // CPU-only checks of host/nlopt_lite.hpp on analytic problems (run by tests/test_nlopt_lite.py).
 #include "../../gaussian_process_liouville_equation_b200/host/nlopt_lite.hpp"
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
@@ -157,6 +158,50 @@ int main()
 		double f = 0.0;
 		o.optimize(x, f);
 		expect(std::abs(f + 1.0316) < 1e-3 && std::abs(std::abs(x[0]) - 0.0898) < 2e-2 && std::abs(std::abs(x[1]) - 0.7126) < 2e-2, "DIRECT-L finds a global minimum of the six-hump camel function");
+	}
+	{
+		// the caller's stop flag (nlopt's force_stop): raised from inside the objective after 25 evaluations, every algorithm
+		// returns at its next iteration; a copy of the optimiser carries the flag along, the subsidiary optimiser too
+		struct Counter
+		{
+			int calls = 0;
+			std::atomic<bool> stop{false};
+		};
+		auto counted = [](const std::vector<double>& x, std::vector<double>& g, void* data)
+		{
+			Counter* c = static_cast<Counter*>(data);
+			if (++c->calls >= 25)
+			{
+				c->stop.store(true);
+			}
+			return rosenbrock(x, g, nullptr);
+		};
+		bool all = true;
+		for (const algorithm a : {LN_NELDERMEAD, LD_SLSQP, AUGLAG_EQ, GN_DIRECT_L})
+		{
+			Counter c;
+			opt o(a, 2);
+			o.set_xtol_rel(1e-14);
+			o.set_ftol_rel(1e-14);
+			if (a == AUGLAG_EQ)
+			{
+				opt sub(LD_SLSQP, 2);
+				sub.set_xtol_rel(1e-14);
+				sub.set_ftol_rel(1e-14);
+				o.set_local_optimizer(sub);
+			}
+			o.set_lower_bounds({-5.0, -5.0});
+			o.set_upper_bounds({5.0, 5.0});
+			o.set_min_objective(counted, &c);
+			o.set_maxeval(100000);
+			o.set_stop_flag(&c.stop);
+			opt running(o); // what Optimization::optimize hands to a stage that runs ahead of time
+			std::vector<double> x{-1.2, 1.0};
+			double f = 0.0;
+			running.optimize(x, f);
+			all = all && c.calls >= 25 && c.calls < 120 && running.get_numevals() == c.calls;
+		}
+		expect(all, "a raised stop flag ends every algorithm within one iteration");
 	}
 	return failures == 0 ? EXIT_SUCCESS : EXIT_FAILURE;
 }
