@@ -59,3 +59,82 @@ def test_capacity_and_bad_arguments():
     assert lib.gple_gate_schedule_automatic(0, 128, None, None, 0) == 6
     assert lib.gple_gate_schedule_automatic(0, -1, None, None, 0) < 0
     assert lib.gple_gate_schedule_automatic(0, 16, None, None, 4) < 0
+
+
+def _load_sim():
+    spec = importlib.util.spec_from_file_location("gate_schedule_sim", os.path.join(ROOT, "profiles", "gate_schedule_sim.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    return sim
+
+
+def test_offline_model_restates_the_reference_kernels():
+    """profiles/gate_schedule_sim.py builds the (composite) covariances itself; they must be the oracle's."""
+    import numpy as np
+
+    from gaussian_process_liouville_equation_b200 import synthetic as syn
+    from oracle import oracle as orc
+
+    sim = _load_sim()
+    X, y = syn.training_set(5, 1, 96, (0.0, syn.P0))
+    Xq = syn.extra_points(5, 1, X, 40, (0.0, syn.P0))[0]
+    tr = np.array([1.0, 0.9 * syn.SIGMA_X, 1.1 * syn.SIGMA_P, 2e-2])
+    tc = np.array([1.0, 1.2, 0.8 * syn.SIGMA_X, 1.1 * syn.SIGMA_P, 0.7, 1.1 * syn.SIGMA_X, 0.9 * syn.SIGMA_P, 2e-2])
+    K, ks, prior, noise = sim.real_model(X, Xq, tr)
+    assert np.abs(K - orc.kernel_real(X, X, tr, True, False)).max() < 1e-14 and np.abs(ks - orc.kernel_real(Xq, X, tr, False, False)).max() < 1e-14
+    assert prior == pytest.approx(K[0, 0], rel=1e-15) and noise == pytest.approx((tr[0] * tr[3]) ** 2, rel=1e-15)
+    Kc, kc, prior_c, noise_c = sim.complex_model(X, Xq, tc)
+    Ko, Kto = orc.kernel_complex(X, X, tc, True, False)
+    ref = 0.5 * np.block([[(Ko + Kto).real, (-Ko + Kto).imag], [(Ko + Kto).imag, (Ko - Kto).real]])  # covariance of [Re y; Im y]
+    assert np.abs(Kc - ref).max() < 1e-14 and prior_c == pytest.approx(Ko[0, 0].real, rel=1e-15)
+    ko, kto = orc.kernel_complex(Xq, X, tc, False, False)
+    rows = 0.5 * np.block([[(ko + kto).real, (-ko + kto).imag], [(ko + kto).imag, (ko - kto).real]])
+    assert np.abs(kc[0::2] - rows[: len(Xq)]).max() < 1e-14 and np.abs(kc[1::2] - rows[len(Xq):]).max() < 1e-14
+
+
+def test_staged_bound_never_contradicts_the_reference_gate():
+    """The three bounds of the bound-gated variance, evaluated on the host along the library's automatic
+    schedule, against the reference's own cutoff (kernel.h:301-332 through the oracle): whatever a stage decides is what the full
+    computation gives -- gate exactly 1 or exactly 0 -- and the undecided queries are the ones with a gate below 1."""
+    import numpy as np
+    import scipy.linalg as sl
+
+    from gaussian_process_liouville_equation_b200 import synthetic as syn
+    from oracle import oracle as orc
+
+    n, centre = 640, (0.0, syn.P0)  # five 128-blocks: stages after 1 and 3 blocks, then the rest
+    X, y = syn.training_set(9, 0, n, centre)
+    Xq = syn.extra_points(9, 0, X, 3000, centre)[0]
+    th = syn.theta_real()
+    k = orc.TrainingKernel(th, X, y)
+    out = k.predict(Xq)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        # the reference's cutoff factor: the prediction is in rescaled labels (RescaleMaximum / max |y|, kernel.cpp:279-280), the
+        # cutoff prediction is scaled back
+        gate = np.where(out["pred"] != 0.0, out["cutoff"] * (10.0 / np.abs(y).max()) / out["pred"], np.nan)
+    K = np.asarray(k.K)
+    f = orc.kernel_real(Xq, X, th, False, False) @ np.asarray(k.v)
+    Z = sl.solve_triangular(np.linalg.cholesky(K), orc.kernel_real(Xq, X, th, False, False).T, lower=True)
+    prior, noise = K[0, 0], (th[0] * th[3]) ** 2
+    f2 = f * f
+    one, zero = f2 >= 4.0 * prior, f2 <= 0.5 * noise
+    open_ = ~(one | zero)
+    schedule = L.gate_schedule_automatic(False, n // 128)
+    assert schedule == [(1, 0), (3, 0)]
+    q = (Z ** 2).reshape(n // 128, 128, -1).sum(1)
+    seen = 0
+    acc = np.zeros(len(Xq))
+    for re_end, _ in schedule:
+        acc = acc + q[seen:re_end].sum(0)
+        seen = re_end
+        decided = open_ & (f2 >= 4.0 * (prior - acc))
+        one |= decided
+        open_ &= ~decided
+    assert one.sum() > 1000 and open_.sum() > 50 and zero.sum() >= 0
+    assert np.all(np.abs(gate[one] - 1.0) < 1e-12)  # decided 1 by a bound: the full computation says 1
+    assert np.all(np.nan_to_num(np.abs(gate[zero]), nan=0.0) == 0.0)  # decided 0 by the noise floor
+    # among the queries no bound decides are all those whose gate is below 1 and above 0: only the exact variance gives it
+    var = prior - (acc + q[seen:].sum(0))
+    band = (f2 < 4.0 * var) & (f2 > var)
+    assert band.sum() > 10 and np.all(open_[band]) and np.all((gate[band] > 0.0) & (gate[band] < 1.0))
+    assert np.abs(var - out["var"]).max() < 1e-9 * prior
