@@ -19,6 +19,7 @@
 #include <cassert>
 #include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <complex>
 #include <condition_variable>
 #include <functional>
@@ -775,12 +776,16 @@ private:
 	static std::uint64_t fingerprint(const ElementTrainingSet& ts)
 	{
 		std::uint64_t h = 1469598103934665603ull;
+		// word-wise (every buffer here is a whole number of 8-byte values): the cache is consulted several times per loss evaluation
 		auto fold = [&h](const void* p, const std::size_t bytes)
 		{
 			const unsigned char* c = static_cast<const unsigned char*>(p);
-			for (std::size_t i = 0; i < bytes; i++)
+			for (std::size_t i = 0; i + 8 <= bytes; i += 8)
 			{
-				h = (h ^ c[i]) * 1099511628211ull;
+				std::uint64_t w;
+				std::memcpy(&w, c + i, 8);
+				h = (h ^ w) * 1099511628211ull;
+				h ^= h >> 29;
 			}
 		};
 		const auto& [X, y] = ts;
