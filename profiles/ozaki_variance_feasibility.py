@@ -8,7 +8,7 @@ below that truncation and are dropped: s (s + 1) / 2 integer GEMMs.  The script 
 error of the posterior variance k** - sum Z^2 (relative to k**) against an 80-bit reference, per number of slices, next to
 the plain FP64 product -- and the int8 throughput a B200 would need to beat the DMMA kernel.
 
-usage: python profiles/ozaki_variance_feasibility.py [N] [queries]"""
+usage: python profiles/ozaki_variance_feasibility.py [N] [queries] [real|complex]"""
 import os
 import sys
 
@@ -21,6 +21,7 @@ from gaussian_process_liouville_equation_b200 import synthetic as syn  # noqa: E
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 Q = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+KIND = sys.argv[3] if len(sys.argv) > 3 else "real"
 BITS = 7
 
 
@@ -57,29 +58,42 @@ def ozaki_product(A, B, s):
 
 
 def main():
-    X, y = syn.training_set(2, 0, N, bench.CENTRE)
-    Xq = syn.extra_points(2, 0, X, Q, bench.CENTRE)[0]
-    sf, lx, lp, sn = bench.THETA_R
+    e = 0 if KIND == "real" else 1
+    X, y = syn.training_set(2, e, N, bench.CENTRE)
+    Xq = syn.extra_points(2, e, X, Q, bench.CENTRE)[0]
 
-    def gauss(A, B):
+    def gauss(A, B, mag2, lx, lp):
         d = ((A[:, None, 0] - B[None, :, 0]) / lx) ** 2 + ((A[:, None, 1] - B[None, :, 1]) / lp) ** 2
-        return sf ** 2 * np.exp(-0.5 * d)
+        return mag2 * np.exp(-0.5 * d)
 
-    K = gauss(X, X) + (sf * sn) ** 2 * np.eye(N)
-    prior = K[0, 0]
-    W = sl.solve_triangular(np.linalg.cholesky(K), np.eye(N), lower=True)
-    ks = gauss(Xq, X)
+    if KIND == "real":
+        sf, lx, lp, sn = bench.THETA_R
+        K = gauss(X, X, sf ** 2, lx, lp) + (sf * sn) ** 2 * np.eye(N)
+        ks = gauss(Xq, X, sf ** 2, lx, lp)
+    else:  # composite [Re; Im] process of the widely-linear complex element (complex_spec of csrc/gpr.cu)
+        th = np.asarray(bench.THETA_C)
+        s2, sr, lr, si, li = th[0] ** 2, th[1], th[2:4], th[4], th[5:7]
+        ss = lr ** 2 + li ** 2
+        lc, sc2, hn = np.sqrt(ss / 2), sr * si * np.prod(2 * lr * li / ss), 0.5 * s2 * th[7] ** 2
+        blocks = lambda A, B: (gauss(A, B, s2 * sr * sr, *lr), gauss(A, B, s2 * si * si, *li), gauss(A, B, s2 * sc2, *lc))  # noqa: E731
+        rr, ii, ri = blocks(X, X)
+        K = np.block([[rr + hn * np.eye(N), ri], [ri.T, ii + hn * np.eye(N)]])
+        qr, qi, qc = blocks(Xq, X)
+        ks = np.vstack([np.hstack([qr, qc]), np.hstack([qc, qi])])  # Re rows, then Im rows
+    prior = K[0, 0] if KIND == "real" else K[0, 0] + K[N, N]
+    W = sl.solve_triangular(np.linalg.cholesky(K), np.eye(len(K)), lower=True)
     ref = (ks.astype(np.longdouble) @ W.T.astype(np.longdouble))  # 64-bit mantissa
-    var_ref = prior - (ref * ref).sum(1)
+    fold = (lambda v: v) if KIND == "real" else (lambda v: v[: len(v) // 2] + v[len(v) // 2:])  # variance of a complex query: Re + Im rows
+    var_ref = prior - fold((ref * ref).sum(1))
     z64 = ks @ W.T
-    var64 = prior - (z64 * z64).sum(1)
-    print(f"# Ozaki splitting of the variance GEMM: real element, N = {N}, {Q} queries, max |W| = {np.abs(W).max():.3g}, cond(K) = {np.linalg.cond(K):.3g}\n")
+    var64 = prior - fold((z64 * z64).sum(1))
+    print(f"# Ozaki splitting of the variance GEMM: {KIND} element, N = {N}, {Q} queries, max |W| = {np.abs(W).max():.3g}, cond(K) = {np.linalg.cond(K):.3g}\n")
     print("| product | integer GEMMs | max error of the variance / k** | max |dZ| |")
     print("|---|---:|---:|---:|")
     print(f"| FP64 (what DMMA computes) | - | {float(np.abs(var64 - var_ref).max() / prior):.2e} | {float(np.abs(z64 - ref).max()):.2e} |")
     for s in (6, 7, 8, 9, 10, 11):
         Z, pairs = ozaki_product(ks, W, s)
-        var = prior - (Z * Z).sum(1)
+        var = prior - fold((Z * Z).sum(1))
         print(f"| {s} slices of {BITS} bits | {pairs} | {float(np.abs(var - var_ref).max() / prior):.2e} | {float(np.abs(Z - ref).max()):.2e} |")
     print("\nBreak-even against the DMMA kernel (32 TFLOP/s executed): an int8 rate of 32 x (integer GEMMs) TOP/s; the nominal dense")
     print("int8 tensor rate of a B200 is 4500 TOP/s.")
